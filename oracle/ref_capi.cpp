@@ -18,6 +18,7 @@
 #include <iostream>
 #include <streambuf>
 #include <fftw3.h>
+#include <omp.h>
 
 #include "bm5d.h"
 #include "bm3d.h"
@@ -33,9 +34,15 @@ using std::vector;
 namespace {
 /* The reference prints progress on cout; silence it unless asked. */
 struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+/* The reference's SAI-selection loops race on shared variables under OpenMP (bm5d.cpp:190-202, 322-334), so
+ * its window schedule is only deterministic with one OpenMP thread: force that unless told otherwise. */
 struct CoutSilencer {
     std::streambuf *old; NullBuf nb;
-    CoutSilencer() : old(nullptr) { if (!getenv("LFBM5D_REF_VERBOSE")) old = std::cout.rdbuf(&nb); }
+    CoutSilencer() : old(nullptr) {
+        if (!getenv("LFBM5D_REF_VERBOSE")) old = std::cout.rdbuf(&nb);
+        const char *t = getenv("LFBM5D_REF_OMP_THREADS");
+        omp_set_num_threads(t ? atoi(t) : 1);
+    }
     ~CoutSilencer() { if (old) std::cout.rdbuf(old); }
 };
 
