@@ -1,0 +1,114 @@
+/* lfbm5d_cuda.h — C ABI of the B200-native LFBM5D denoising hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types. The C++
+ * adapters in lfbm5d_b200/csrc/lfbm5d_host.{h,cpp} wrap it with the reference's own signatures
+ * (run_bm5d_1st_step / run_bm5d_2nd_step, bm5d.h:11-62; run_bm3d_LF, bm3d_LF.h:10-35) and
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Semantics follow the reference with nb_threads == 1: results do not depend on
+ * nb_threads, which is accepted and ignored. All functions return 0 (EXIT_SUCCESS) or 1
+ * (EXIT_FAILURE) like the reference's drivers; lfbm5d_last_error() gives the reason.
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef LFBM5D_CUDA_H
+#define LFBM5D_CUDA_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enum values = the reference's #defines (main.cpp:20-32) */
+enum { LFBM5D_YUV = 0, LFBM5D_YCBCR = 1, LFBM5D_OPP = 2, LFBM5D_RGB = 3, LFBM5D_ID = 4, LFBM5D_DCT = 5, LFBM5D_SADCT = 6,
+       LFBM5D_BIOR = 7, LFBM5D_HADAMARD = 8, LFBM5D_HAAR = 9, LFBM5D_NONE = 10, LFBM5D_ROWMAJOR = 11, LFBM5D_COLMAJOR = 12 };
+
+typedef struct lfbm5d_ctx lfbm5d_ctx;
+
+/* POD mirror of the argument list of run_bm5d_1st_step / run_bm5d_2nd_step (bm5d.h:11-62). */
+typedef struct lfbm5d_params {
+    float    sigma;
+    float    lambda;        /* lambdaHard5D; ignored by step 2 */
+    unsigned ang_major;     /* LFBM5D_ROWMAJOR / LFBM5D_COLMAJOR */
+    unsigned awidth, aheight;
+    unsigned an;            /* anHard / anWien: half size of the angular search window */
+    unsigned width, height, chnls;
+    unsigned N;             /* NHard / NWien */
+    unsigned nSim, nDisp;
+    unsigned k;             /* kHard / kWien */
+    unsigned p;             /* pHard / pWien */
+    unsigned useSD;
+    unsigned tau_2D, tau_4D, tau_5D;
+    unsigned color_space;
+    unsigned nb_threads;    /* accepted, ignored (always nb_threads == 1 semantics) */
+} lfbm5d_params;
+
+/* POD mirror of run_bm3d_LF's argument list (bm3d_LF.h:10-35). */
+typedef struct lfbm3d_params {
+    float    sigma;
+    unsigned asize;         /* number of SAIs */
+    unsigned width, height, chnls;
+    unsigned nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien;
+    unsigned useSD_h, useSD_w;
+    unsigned tau_2D_hard, tau_2D_wien;
+    float    lambdaHard3D;
+    unsigned color_space;
+    unsigned nb_threads;
+} lfbm3d_params;
+
+typedef struct lfbm5d_stats {
+    unsigned long long kernel_launches;   /* kernels of this library launched since the last reset */
+    unsigned           window_passes;     /* core calls (bm5d_{1st,2nd}_step equivalents) since the last reset */
+    float              ms_block_matching; /* device time (CUDA events) since the last reset, when timing is enabled */
+    float              ms_groups;         /* gather + transforms + shrinkage + aggregation */
+    float              ms_other;
+    float              ms_sat;            /* summed-area kernel alone (dominant block-matching kernel) */
+} lfbm5d_stats;
+
+int  lfbm5d_create(lfbm5d_ctx **out, int device);
+void lfbm5d_destroy(lfbm5d_ctx *ctx);
+const char *lfbm5d_last_error(void);
+void lfbm5d_reset_stats(lfbm5d_ctx *ctx);
+void lfbm5d_get_stats(lfbm5d_ctx *ctx, lfbm5d_stats *out);
+void lfbm5d_enable_timing(lfbm5d_ctx *ctx, int on);   /* per-phase CUDA-event timing (adds synchronisation) */
+/* cudaStream_t the library launches on, as void* (for callers that time with their own events) */
+void *lfbm5d_stream(lfbm5d_ctx *ctx);
+
+/* ---- reference-facing entry points: HOST buffers, copies inside ---------------------------------
+ * noisy[st] / basic[st] / denoised[st]: asize caller-owned host arrays of width*height*chnls floats,
+ * planar (c*W*H + i*W + j), st ordered per ang_major, like the reference's vector<vector<float>>.
+ * Side effects as in the reference: noisy (and basic in step 2) come back colour-round-tripped
+ * (bm5d.cpp:133, 711-714, 827-830, 1414-1419). Entries of masked-out SAIs are not touched. */
+int lfbm5d_step1(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, const unsigned *sai_mask,
+                 float *const *basic_out);
+int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, float *const *basic_io,
+                 const unsigned *sai_mask, float *const *denoised_out);
+int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, const unsigned *sai_mask,
+               float *const *basic_out, float *const *denoised_out);
+
+/* ---- device-resident variants: d_* are device pointers to [asize][chnls][height][width] floats --- */
+int lfbm5d_step1_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, const unsigned *sai_mask, float *d_basic_out);
+int lfbm5d_step2_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io,
+                        const unsigned *sai_mask, float *d_denoised_out);
+/* stop after this many window passes per step (0 = run to completion); for bounded measurements only */
+void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned max_passes);
+
+/* ---- parity/debug exports (used by tests only) ---------------------------------------------------
+ * One window pass (the reference's bm5d_1st_step / bm5d_2nd_step, `pst == cst` branch) on HOST padded
+ * buffers [A][chnls][h_b][w_b], A = (2*an+1)^2, h_b = height + 2*(nSim+nDisp); p->width/height are the
+ * UNPADDED sizes. num/den are updated in place. Optional outputs (may be NULL): self matches of the
+ * reference SAI as count[h_b*w_b], idx[h_b*w_b*(N+1)]; stereo results first[A][h_b*w_b], shape[A][h_b*w_b]
+ * in the layout of oracle/lfbm5d_oracle.h: orc_pass. */
+int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
+                      float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw,
+                      unsigned pst, unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
+/* Block matching alone on one padded channel-0 plane (host pointers). */
+int lfbm5d_debug_bm_self(lfbm5d_ctx *ctx, const float *img, unsigned w_b, unsigned h_b, unsigned k, unsigned N, unsigned nHW,
+                         unsigned nSim, unsigned p, float tauMatch, unsigned *out_count, unsigned *out_idx);
+int lfbm5d_debug_bm_stereo(lfbm5d_ctx *ctx, const float *img1, const float *img2, unsigned w_b, unsigned h_b, unsigned k,
+                           unsigned nHW, unsigned nDisp, float tauMatch, unsigned *out_first, unsigned *out_shape);
+/* Window schedule of the last step call: (processed st, min_s, min_t, core calls) per window pass. */
+unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+"""lfbm5d_b200 — B200-native (sm_100a CUDA) LFBM5D light-field denoising hot path.
+
+This package is a thin ctypes view of the C ABI in include/lfbm5d_cuda.h (the drop-in boundary);
+the C++ adapters with the reference's own signatures live in csrc/lfbm5d_host.{h,cpp}.
+There is no CPU fallback: if the CUDA library is missing or no GPU is present, calls raise.
+
+Reference interface mirrored (V-Sense/LFBM5D): run_bm5d_1st_step / run_bm5d_2nd_step (bm5d.h:11-62),
+run_bm3d_LF (bm3d_LF.h:10-35); enum values are the reference's #defines (main.cpp:20-32).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+YUV, YCBCR, OPP, RGB, ID, DCT, SADCT, BIOR, HADAMARD, HAAR, NONE, ROWMAJOR, COLMAJOR = range(13)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblfbm5d_cuda.so")
+
+
+class Params(C.Structure):
+    """POD mirror of lfbm5d_params (include/lfbm5d_cuda.h)."""
+    _fields_ = [("sigma", C.c_float), ("lambda_", C.c_float), ("ang_major", C.c_uint), ("awidth", C.c_uint),
+                ("aheight", C.c_uint), ("an", C.c_uint), ("width", C.c_uint), ("height", C.c_uint), ("chnls", C.c_uint),
+                ("N", C.c_uint), ("nSim", C.c_uint), ("nDisp", C.c_uint), ("k", C.c_uint), ("p", C.c_uint),
+                ("useSD", C.c_uint), ("tau_2D", C.c_uint), ("tau_4D", C.c_uint), ("tau_5D", C.c_uint),
+                ("color_space", C.c_uint), ("nb_threads", C.c_uint)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_ulonglong), ("window_passes", C.c_uint), ("ms_block_matching", C.c_float),
+                ("ms_groups", C.c_float), ("ms_other", C.c_float), ("ms_sat", C.c_float)]
+
+
+EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset_stats", "lfbm5d_get_stats",
+           "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
+           "lfbm5d_step2_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_bm_self",
+           "lfbm5d_debug_bm_stereo", "lfbm5d_debug_schedule"]
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.lfbm5d_last_error.restype = C.c_char_p
+        _lib.lfbm5d_stream.restype = C.c_void_p
+        _lib.lfbm5d_debug_schedule.restype = C.c_uint
+    return _lib
+
+
+def make_params(sigma, lam, aw, ah, an, width, height, chnls, N, nSim, nDisp, k, p, tau_2D, tau_4D, tau_5D,
+                color_space=OPP, ang_major=ROWMAJOR, useSD=0, nb_threads=1):
+    return Params(sigma, lam, ang_major, aw, ah, an, width, height, chnls, N, nSim, nDisp, k, p, useSD, tau_2D, tau_4D,
+                  tau_5D, color_space, nb_threads)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _up(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_uint))
+
+
+class LFBM5D(object):
+    """One context per GPU. Host-array methods copy in and out (the reference-facing path)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        if self.lib.lfbm5d_create(C.byref(self.ctx), int(device)) != 0:
+            raise RuntimeError("lfbm5d_create: " + self.error())
+
+    def error(self):
+        return self.lib.lfbm5d_last_error().decode()
+
+    def close(self):
+        if self.ctx:
+            self.lib.lfbm5d_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- bookkeeping --------------------------------------------------------------------------
+    def reset_stats(self):
+        self.lib.lfbm5d_reset_stats(self.ctx)
+
+    def stats(self):
+        s = Stats()
+        self.lib.lfbm5d_get_stats(self.ctx, C.byref(s))
+        return s
+
+    def enable_timing(self, on=True):
+        self.lib.lfbm5d_enable_timing(self.ctx, int(on))
+
+    def set_max_passes(self, n):
+        self.lib.lfbm5d_set_max_passes(self.ctx, int(n))
+
+    def stream(self):
+        return self.lib.lfbm5d_stream(self.ctx)
+
+    def schedule(self, max_entries=4096):
+        out = np.zeros((max_entries, 4), np.uint32)
+        n = self.lib.lfbm5d_debug_schedule(self.ctx, _up(out), max_entries)
+        return out[:n]
+
+    # -- host-buffer entry points (like run_bm5d_1st_step / run_bm5d_2nd_step) --------------------
+    @staticmethod
+    def _ptrs(arr):
+        n = arr.shape[0]
+        return (C.POINTER(C.c_float) * n)(*[_fp(arr[i]) for i in range(n)])
+
+    def step1(self, prm, noisy, mask):
+        """noisy [asize, C, H, W] float32 RGB -> (basic, noisy round-tripped through the colour space)."""
+        n = np.ascontiguousarray(noisy, np.float32).copy()
+        basic = np.zeros_like(n)
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_step1(self.ctx, C.byref(prm), self._ptrs(n), _up(m), self._ptrs(basic)) != 0:
+            raise RuntimeError("lfbm5d_step1: " + self.error())
+        return basic, n
+
+    def step2(self, prm, noisy, basic, mask):
+        n = np.ascontiguousarray(noisy, np.float32).copy()
+        b = np.ascontiguousarray(basic, np.float32).copy()
+        out = np.zeros_like(n)
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_step2(self.ctx, C.byref(prm), self._ptrs(n), self._ptrs(b), _up(m), self._ptrs(out)) != 0:
+            raise RuntimeError("lfbm5d_step2: " + self.error())
+        return out, b, n
+
+    # -- device-resident entry points (raw device pointers, e.g. torch tensors' data_ptr()) -------
+    def step1_device(self, prm, d_noisy, mask, d_basic):
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_step1_device(self.ctx, C.byref(prm), C.c_void_p(d_noisy), _up(m), C.c_void_p(d_basic)) != 0:
+            raise RuntimeError("lfbm5d_step1_device: " + self.error())
+
+    def step2_device(self, prm, d_noisy, d_basic, mask, d_out):
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_step2_device(self.ctx, C.byref(prm), C.c_void_p(d_noisy), C.c_void_p(d_basic), _up(m),
+                                        C.c_void_p(d_out)) != 0:
+            raise RuntimeError("lfbm5d_step2_device: " + self.error())
+
+    # -- parity/debug: one window pass on padded host buffers --------------------------------------
+    def debug_pass(self, step, prm, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, debug=False):
+        A, Cn, hb, wb = noisy_sym.shape
+        ns = np.ascontiguousarray(noisy_sym, np.float32)
+        bs = None if basic_sym is None else np.ascontiguousarray(basic_sym, np.float32)
+        num = np.ascontiguousarray(num_sym, np.float32).copy()
+        den = np.ascontiguousarray(den_sym, np.float32).copy()
+        dbg = [None] * 4
+        if debug:
+            dbg = [np.zeros(hb * wb, np.uint32), np.zeros((hb * wb, prm.N + 1), np.uint32),
+                   np.zeros((A, hb * wb), np.uint32), np.zeros((A, hb * wb), np.uint32)]
+        rc = self.lib.lfbm5d_debug_pass(self.ctx, int(step), C.byref(prm), _fp(ns), None if bs is None else _fp(bs),
+                                        _fp(num), _fp(den), _up(np.ascontiguousarray(mask, np.uint32)),
+                                        _up(np.ascontiguousarray(proc, np.uint32)), int(pst), *[_up(d) for d in dbg])
+        if rc != 0:
+            raise RuntimeError("lfbm5d_debug_pass: " + self.error())
+        return (num, den, dbg) if debug else (num, den)

@@ -1,0 +1,43 @@
+// Common definitions of the LFBM5D CUDA path (sm_100a). Compiled with -fmad=false: every a*b+c in this
+// translation unit is a separate multiply and add, like the reference's x86-64 build; fused multiply-adds
+// appear only where written explicitly (fmaf in the DCT passes, matching oracle DCT mode 0).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LF_MAXK      16      // largest patch side handled by the transform kernels
+#define LF_MAXASW    3       // angular window side (2*an+1), an <= 1
+#define LF_MAXA      (LF_MAXASW * LF_MAXASW)
+#define LF_MAXN      32      // largest number of similar patches
+#define LF_MAXNS2    169     // (2*nDisp+1)^2, nDisp <= 6
+#define LF_SQRT2_INV_F ((float) 0.7071067811865475)
+#define LF_SQRT2_F     ((float) 1.414213562373095)
+
+// Per-step constants. Filled on the host with the reference's expressions (bm3d.cpp:1101-1169 preProcess,
+// core:3191-3252 preProcess_4d / preProcess_4d_sadct, utilities.cpp:633-684 estimate_sigma) and the FFTW
+// REDFT10/REDFT01 cosine tables (oracle DCT mode 0), then copied to constant memory.
+struct LfTables {
+    float dct2f[LF_MAXK * LF_MAXK];      // [kk*k + j] = (float)(2 cos(pi (j+1/2) kk / k))
+    float dct2i[LF_MAXK * LF_MAXK];      // [kk*k + j] = j ? (float)(2 cos(pi j (kk+1/2) / k)) : 1
+    float cn2[LF_MAXK * LF_MAXK], cni2[LF_MAXK * LF_MAXK], kaiser[LF_MAXK * LF_MAXK];
+    float coef2inv;                      // 1 / (2k)
+    float dctaf[LF_MAXASW][LF_MAXASW * LF_MAXASW];   // [n-1][kk*n + j], 1-D tables for lengths 1..asw
+    float dctai[LF_MAXASW][LF_MAXASW * LF_MAXASW];
+    float cn4[LF_MAXA], cni4[LF_MAXA];
+    float coef4inv;                      // 1 / (sqrt(aw) sqrt(ah) 2)
+    float cnsa[LF_MAXASW][LF_MAXASW], cnisa[LF_MAXASW][LF_MAXASW];   // [n-2][t]
+    float coefsa_inv[LF_MAXASW + 1];     // [n] = 0.5 (float)SQRT2_INV / sqrt(n)
+    float lpd[10], hpd[10], lpr[10], hpr[10];
+    float sigma[3], sigma2[3];
+    float thr[3][8];                     // hard threshold per channel and log2(nSx)
+    float hadcoef[8];                    // 1 / nSx
+};
+
+__constant__ LfTables c_tab;
+
+struct LfWindow {
+    int      st[LF_MAXA];        // global SAI index of each window slot
+    unsigned mask[LF_MAXA];
+    unsigned proc[LF_MAXA];
+    int      A;
+};

@@ -1,0 +1,540 @@
+// 5-D group processing: gather -> 2-D spatial transform -> angular (SA-)DCT -> 1-D transform along the similar
+// patches -> hard threshold / Wiener shrinkage -> inverses -> weighted aggregation. One CTA per reference patch,
+// one colour channel at a time in shared memory. Restates core:277-528 (step 1) and :1054-1329 (step 2).
+#pragma once
+#include "common.cuh"
+
+struct GroupArgs {
+    int C, asw, A, k, log2k, N, w, h, pst, nc;
+    int RS, PS;                       // shared-memory row stride / patch stride (floats)
+    unsigned tau_2D, tau_4D, tau_5D;
+    const int *rows, *cols;
+    const unsigned *bm_count, *bm_idx;            // [R], [R*(N+1)]
+    const unsigned *first;                        // [A][plane] disparity argmin
+    const unsigned char *shape;                   // [A][plane]
+    const float *nsym, *bsym;                     // [A][C][plane]
+    float *numsym, *densym;
+    LfWindow win;
+};
+
+struct GroupShape {
+    unsigned mask[LF_MAXA], idx[LF_MAXA], idx_col[LF_MAXA], mask_dct[LF_MAXA];
+    unsigned row_size[LF_MAXASW], col_size[LF_MAXASW];
+    int use_sadct;
+};
+
+// ---- 1-D transforms along the similar patches (lib_transforms.cpp:290-321, :403-471), fully unrolled ----
+template <int NS> __device__ __forceinline__ void lf_haar_fwd(float *v)
+{
+    float tmp[NS > 1 ? NS : 1];
+#pragma unroll
+    for (int N = NS; N >= 2; N >>= 1) {
+        const int n = N / 2;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float a = v[2 * i], b = v[2 * i + 1];
+            tmp[i] = (a + b) * LF_SQRT2_INV_F;
+            tmp[n + i] = (a - b) * LF_SQRT2_INV_F;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = tmp[i];
+    }
+}
+template <int NS> __device__ __forceinline__ void lf_haar_inv(float *v)
+{
+    float tmp[NS > 1 ? NS : 1];
+#pragma unroll
+    for (int n = 1; n < NS; n *= 2) {
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float a = v[i], b = v[n + i];
+            tmp[2 * i] = (a + b) * LF_SQRT2_INV_F;
+            tmp[2 * i + 1] = (a - b) * LF_SQRT2_INV_F;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * n; ++i) v[i] = tmp[i];
+    }
+}
+template <int NS> __device__ __forceinline__ void lf_hadamard(float *v)
+{
+    float tmp[NS > 1 ? NS : 1];
+#pragma unroll
+    for (int len = NS; len >= 2; len >>= 1) {
+        const int n = len / 2;
+#pragma unroll
+        for (int base = 0; base < NS; base += len) {
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float a = v[base + 2 * i], b = v[base + 2 * i + 1];
+                tmp[base + i] = a + b;
+                tmp[base + n + i] = a - b;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v[i] = tmp[i];
+    }
+}
+
+__device__ __forceinline__ float lf_block_sum_f(float v, float *sh)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) r += sh[i];
+    return r;
+}
+
+// ---- 5th-dimension filtering of one (st, pq) vector; returns this thread's contribution to weight_table[c] ----
+template <int STEP, int NS>
+__device__ __forceinline__ float lf_filter5d(float *X, float *E, int base, int nstride, unsigned tau_5D, bool shrink, int c, int lg)
+{
+    float vo[NS], ve[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) vo[n] = X[base + n * nstride];
+    if (STEP == 2) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) ve[n] = E[base + n * nstride];
+    }
+    const bool haar = tau_5D == 9;
+    if (NS > 1) {
+        if (haar) { lf_haar_fwd<NS>(vo); if (STEP == 2) lf_haar_fwd<NS>(ve); }
+        else { lf_hadamard<NS>(vo); if (STEP == 2) lf_hadamard<NS>(ve); }
+    }
+    float wsum = 0.f;
+    if (shrink) {
+        if (STEP == 1) {
+            const float T = haar ? c_tab.thr[c][0] : c_tab.thr[c][lg];
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                if (fabsf(vo[n]) > T) wsum += 1.0f; else vo[n] = 0.0f;
+            }
+        } else {
+            const float s2 = c_tab.sigma2[c];
+            const float hc = c_tab.hadcoef[lg];
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                float value;
+                if (haar) {
+                    value = ve[n] * ve[n];
+                    value = value / (value + s2);
+                    ve[n] = vo[n] * value;
+                } else {
+                    value = ve[n] * ve[n] * hc;
+                    value = value / (value + s2);
+                    ve[n] = vo[n] * value * hc;
+                }
+                wsum += value;
+            }
+        }
+    }
+    float *out = STEP == 1 ? vo : ve;
+    if (NS > 1) {
+        if (haar) lf_haar_inv<NS>(out);
+        else {
+            lf_hadamard<NS>(out);
+            if (STEP == 1) {
+                const float hc = c_tab.hadcoef[lg];
+#pragma unroll
+                for (int n = 0; n < NS; ++n) out[n] *= hc;
+            }
+        }
+    }
+    float *dst = STEP == 1 ? X : E;
+#pragma unroll
+    for (int n = 0; n < NS; ++n) dst[base + n * nstride] = out[n];
+    return wsum;
+}
+
+// ---- angular transforms of one (n, pq) vector v[A] (st fastest) ----
+template <int ASW> __device__ __forceinline__ void lf_dct4_fwd(float *v)
+{
+    const float *T = c_tab.dctaf[ASW - 1];
+    float y[ASW * ASW];
+#pragma unroll
+    for (int s = 0; s < ASW; ++s)
+#pragma unroll
+        for (int kk = 0; kk < ASW; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < ASW; ++t) acc = fmaf(v[s * ASW + t], T[kk * ASW + t], acc);
+            y[s * ASW + kk] = acc;
+        }
+#pragma unroll
+    for (int t = 0; t < ASW; ++t)
+#pragma unroll
+        for (int kk = 0; kk < ASW; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < ASW; ++s) acc = fmaf(y[s * ASW + t], T[kk * ASW + s], acc);
+            v[kk * ASW + t] = acc * c_tab.cn4[kk * ASW + t];
+        }
+}
+template <int ASW> __device__ __forceinline__ void lf_dct4_inv(float *v)
+{
+    const float *T = c_tab.dctai[ASW - 1];
+    float a[ASW * ASW], y[ASW * ASW];
+#pragma unroll
+    for (int st = 0; st < ASW * ASW; ++st) a[st] = v[st] * c_tab.cni4[st];
+#pragma unroll
+    for (int s = 0; s < ASW; ++s)
+#pragma unroll
+        for (int kk = 0; kk < ASW; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < ASW; ++t) acc = fmaf(a[s * ASW + t], T[kk * ASW + t], acc);
+            y[s * ASW + kk] = acc;
+        }
+#pragma unroll
+    for (int t = 0; t < ASW; ++t)
+#pragma unroll
+        for (int kk = 0; kk < ASW; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int s = 0; s < ASW; ++s) acc = fmaf(y[s * ASW + t], T[kk * ASW + s], acc);
+            v[kk * ASW + t] = acc * c_tab.coef4inv;
+        }
+}
+// generic 1-D r2r of length n (1..ASW) on a small array
+__device__ __forceinline__ void lf_r2r_small(const float *in, float *out, int n, bool fwd)
+{
+    const float *T = fwd ? c_tab.dctaf[n - 1] : c_tab.dctai[n - 1];
+    for (int kk = 0; kk < n; ++kk) {
+        float acc = 0.f;
+        for (int j = 0; j < n; ++j) acc = fmaf(in[j], T[kk * n + j], acc);
+        out[kk] = acc;
+    }
+}
+// shape-adaptive variants (core:1969-2116, :2131-2264); rare path, generic code
+__device__ inline void lf_sadct_fwd(float *v, const GroupShape &sh, int asw)
+{
+    float a[LF_MAXASW], b[LF_MAXASW];
+    for (int s = 0; s < asw; ++s) {
+        const int n = sh.row_size[s];
+        if (n == 1) v[s * asw] = v[s * asw + sh.idx[s * asw]];
+        else if (n > 1) {
+            for (int t = 0; t < n; ++t) a[t] = v[s * asw + sh.idx[s * asw + t]];
+            lf_r2r_small(a, b, n, true);
+            for (int t = 0; t < n; ++t) v[s * asw + t] = b[t] * c_tab.cnsa[n - 2][t];
+        }
+    }
+    for (int t = 0; t < asw; ++t) {
+        const int n = sh.col_size[t];
+        if (n == 1) v[t] = v[sh.idx_col[t] * asw + t];
+        else if (n > 1) {
+            for (int s = 0; s < n; ++s) a[s] = v[sh.idx_col[s * asw + t] * asw + t];
+            lf_r2r_small(a, b, n, true);
+            for (int s = 0; s < n; ++s) v[s * asw + t] = b[s] * c_tab.cnsa[n - 2][s];
+        }
+    }
+    const float coef = 0.5f * LF_SQRT2_INV_F;
+    for (int st = 0; st < asw * asw; ++st) v[st] *= (float) sh.mask_dct[st] * coef;
+}
+__device__ inline void lf_sadct_inv(float *v, const GroupShape &sh, int asw)
+{
+    float a[LF_MAXASW], b[LF_MAXASW];
+    const float c2 = 2.0f * LF_SQRT2_F;
+    for (int t = 0; t < asw; ++t) {
+        const int n = sh.col_size[t];
+        if (n == 1) v[sh.idx_col[t] * asw + t] = v[t] * c2;
+        else if (n > 1) {
+            for (int s = 0; s < n; ++s) a[s] = v[s * asw + t] * c_tab.cnisa[n - 2][s] * c2;
+            lf_r2r_small(a, b, n, false);
+            const float coef = c_tab.coefsa_inv[n];
+            for (int s = 0; s < n; ++s) v[sh.idx_col[s * asw + t] * asw + t] = b[s] * coef;
+        }
+    }
+    for (int s = 0; s < asw; ++s) {
+        const int n = sh.row_size[s];
+        if (n == 1) v[s * asw + sh.idx[s * asw]] = v[s * asw];
+        else if (n > 1) {
+            for (int t = 0; t < n; ++t) a[t] = v[s * asw + t] * c_tab.cnisa[n - 2][t];
+            lf_r2r_small(a, b, n, false);
+            const float coef = c_tab.coefsa_inv[n];
+            for (int t = 0; t < n; ++t) v[s * asw + sh.idx[s * asw + t]] = b[t] * coef;
+        }
+    }
+    for (int st = 0; st < asw * asw; ++st) v[st] = v[st] * (float) sh.mask[st];
+}
+
+// ---- 2-D spatial transforms, in place on npatch patches stored with row stride RS / patch stride PS ----
+template <int K> __device__ __forceinline__ void lf_dct2d(float *B, int npatch, int RS, int PS, bool fwd)
+{
+    const float *T = fwd ? c_tab.dct2f : c_tab.dct2i;
+    for (int item = threadIdx.x; item < npatch * K; item += blockDim.x) {      // rows (contiguous dimension first)
+        float *row = B + (item / K) * PS + (item % K) * RS;
+        const int p = item % K;
+        float v[K], o[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = fwd ? row[j] : row[j] * c_tab.cni2[p * K + j];
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc = fmaf(v[j], T[kk * K + j], acc);
+            o[kk] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) row[j] = o[j];
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < npatch * K; item += blockDim.x) {      // columns
+        float *col = B + (item / K) * PS + (item % K);
+        const int q = item % K;
+        float v[K], o[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) v[j] = col[j * RS];
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc = fmaf(v[j], T[kk * K + j], acc);
+            o[kk] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) col[j * RS] = fwd ? o[j] * c_tab.cn2[j * K + q] : c_tab.coef2inv * o[j];
+    }
+    __syncthreads();
+}
+
+// Bior1.5 full decomposition / reconstruction (lib_transforms.cpp:46-204); one thread per (patch, line),
+// all indices compile-time so that a line lives in registers.
+template <int N1> __device__ __forceinline__ void lf_bior_line_fwd(float *x, int stride)
+{
+    float v[N1], o[N1];
+    constexpr int N2 = N1 / 2;
+#pragma unroll
+    for (int j = 0; j < N1; ++j) v[j] = x[j * stride];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) {
+        float vl = 0.0f, vh = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            const float xv = v[(t + 2 * j + 4 * N1 - 4) % N1];      // periodic extension by 4 samples (per_ext_ind)
+            vl += xv * c_tab.lpd[t];
+            if (t == 4 || t == 5) vh += xv * c_tab.hpd[t];           // the other high-pass taps are exactly zero
+        }
+        o[j] = vl; o[j + N2] = vh;
+    }
+#pragma unroll
+    for (int j = 0; j < N1; ++j) x[j * stride] = o[j];
+}
+template <int N1> __device__ __forceinline__ void lf_bior_line_inv(float *x, int stride)
+{
+    float v[N1], o[N1];
+    constexpr int N2 = N1 / 2;
+#pragma unroll
+    for (int j = 0; j < N1; ++j) v[j] = x[j * stride];
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        float vl = 0.0f, vh = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+            const float xv = v[(t * N2 + i) % N1];                    // extension by 4*N2 = 2*N1 samples: index mod N1
+            if (t == 4 || t == 5) vl += c_tab.lpr[t] * xv;            // the other low-pass reconstruction taps are zero
+            vh += c_tab.hpr[t] * xv;
+        }
+        o[2 * i] = vh; o[2 * i + 1] = vl;
+    }
+#pragma unroll
+    for (int j = 0; j < N1; ++j) x[j * stride] = o[j];
+}
+template <int N1> __device__ __forceinline__ void lf_bior_level(float *B, int npatch, int RS, int PS, bool fwd)
+{
+    if (fwd) {
+        for (int item = threadIdx.x; item < npatch * N1; item += blockDim.x)
+            lf_bior_line_fwd<N1>(B + (item / N1) * PS + (item % N1) * RS, 1);        // rows
+        __syncthreads();
+        for (int item = threadIdx.x; item < npatch * N1; item += blockDim.x)
+            lf_bior_line_fwd<N1>(B + (item / N1) * PS + (item % N1), RS);            // columns
+        __syncthreads();
+    } else {
+        for (int item = threadIdx.x; item < npatch * N1; item += blockDim.x)
+            lf_bior_line_inv<N1>(B + (item / N1) * PS + (item % N1), RS);            // columns first
+        __syncthreads();
+        for (int item = threadIdx.x; item < npatch * N1; item += blockDim.x)
+            lf_bior_line_inv<N1>(B + (item / N1) * PS + (item % N1) * RS, 1);        // then rows
+        __syncthreads();
+    }
+}
+template <int K> __device__ __forceinline__ void lf_bior2d(float *B, int npatch, int RS, int PS, bool fwd)
+{
+    if (fwd) {
+        if (K >= 16) lf_bior_level<16>(B, npatch, RS, PS, true);
+        if (K >= 8) lf_bior_level<8>(B, npatch, RS, PS, true);
+        lf_bior_level<4>(B, npatch, RS, PS, true);
+        lf_bior_level<2>(B, npatch, RS, PS, true);
+    } else {
+        lf_bior_level<2>(B, npatch, RS, PS, false);
+        lf_bior_level<4>(B, npatch, RS, PS, false);
+        if (K >= 8) lf_bior_level<8>(B, npatch, RS, PS, false);
+        if (K >= 16) lf_bior_level<16>(B, npatch, RS, PS, false);
+    }
+}
+
+__device__ __forceinline__ void lf_t2d(float *B, int npatch, const GroupArgs &g, bool fwd)
+{
+    if (g.tau_2D == 5) {
+        if (g.k == 8) lf_dct2d<8>(B, npatch, g.RS, g.PS, fwd); else lf_dct2d<16>(B, npatch, g.RS, g.PS, fwd);
+    } else if (g.tau_2D == 7) {
+        if (g.k == 8) lf_bior2d<8>(B, npatch, g.RS, g.PS, fwd); else lf_bior2d<16>(B, npatch, g.RS, g.PS, fwd);
+    }
+}
+
+template <int STEP, int ASW>
+__global__ void __launch_bounds__(256) k_groups(GroupArgs g)
+{
+    extern __shared__ float smem[];
+    __shared__ GroupShape sh;
+    __shared__ float red[8];
+    __shared__ unsigned spos[LF_MAXN * LF_MAXA];
+    constexpr int A = ASW * ASW;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int r = blockIdx.x;
+    const int k = g.k, k2 = k * k, w = g.w;
+    const size_t plane = (size_t) g.w * g.h;
+    const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
+    const int nSx = (int) g.bm_count[r];
+    const int lg = 31 - __clz(nSx);
+    const int PS = g.PS, RS = g.RS;
+    float *X = smem;
+    float *E = smem + (size_t) g.N * A * PS;      // step 2 only (N >= nSx except the duplicated single match: N >= 2)
+
+    for (int t = tid; t < nSx * A; t += nth) {
+        const int n = t / A, st = t - n * A;
+        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
+        spos[t] = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
+    }
+    if (tid == 0) {
+        unsigned size = 0;
+        for (int st = 0; st < A; ++st) {
+            const unsigned m = (st == g.pst) ? 1u : (g.win.mask[st] ? (unsigned) g.shape[(size_t) st * plane + k_r] : 0u);
+            sh.mask[st] = m; size += m;
+            sh.idx[st] = 0; sh.idx_col[st] = 0; sh.mask_dct[st] = 0;
+        }
+        sh.use_sadct = (g.tau_4D == 6) && (size != (unsigned) A);
+        if (g.tau_4D == 6) {
+            unsigned mask_col[LF_MAXA];
+            for (int st = 0; st < A; ++st) mask_col[st] = 0;
+            for (int s = 0; s < ASW; ++s) {
+                unsigned rr = 0;
+                for (int t = 0; t < ASW; ++t) if (sh.mask[s * ASW + t]) sh.idx[s * ASW + rr++] = t;
+                sh.row_size[s] = rr;
+                for (unsigned t = 0; t < rr; ++t) mask_col[s * ASW + t] = 1;
+            }
+            for (int t = 0; t < ASW; ++t) {
+                unsigned rr = 0;
+                for (int s = 0; s < ASW; ++s) if (mask_col[s * ASW + t]) sh.idx_col[(rr++) * ASW + t] = s;
+                sh.col_size[t] = rr;
+                for (unsigned s = 0; s < rr; ++s) sh.mask_dct[s * ASW + t] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    const bool use_sadct = sh.use_sadct != 0;
+    const int npatch = nSx * A;
+
+    for (int c = 0; c < g.C; ++c) {
+        // ---- gather (core:286-299): raw patches; a patch whose column is w-k reads as zeros (core:1697) ----
+        for (int t = tid; t < npatch * k2; t += nth) {
+            const int pa = t >> (2 * g.log2k), pq = t & (k2 - 1);
+            const int p = pq >> g.log2k, q = pq & (k - 1);
+            const int st = pa % A;
+            const unsigned pos = spos[pa];
+            float xv = 0.f, ev = 0.f;
+            if (g.win.mask[st] && (int) (pos % (unsigned) w) < w - k) {
+                const size_t src = ((size_t) st * g.C + c) * plane + pos + (size_t) p * w + q;
+                xv = g.nsym[src];
+                if (STEP == 2) ev = g.bsym[src];
+            }
+            X[pa * PS + p * RS + q] = xv;
+            if (STEP == 2) E[pa * PS + p * RS + q] = ev;
+        }
+        __syncthreads();
+        // ---- 2-D spatial transform; patches that read as zeros stay zero under any of the transforms ----
+        lf_t2d(X, npatch, g, true);
+        if (STEP == 2) lf_t2d(E, npatch, g, true);
+        // ---- angular transform (core:354-360) ----
+        if (g.tau_4D != 4) {
+            for (int t = tid; t < nSx * k2; t += nth) {
+                const int n = t >> (2 * g.log2k), pq = t & (k2 - 1);
+                const int off = n * A * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+                for (int rep = 0; rep < STEP; ++rep) {
+                    float *B = rep == 0 ? X : E;
+                    float v[A];
+#pragma unroll
+                    for (int st = 0; st < A; ++st) v[st] = B[off + st * PS];
+                    if (use_sadct) {        // rare: keep the dynamically indexed copy away from the register-resident one
+                        float u[A];
+#pragma unroll
+                        for (int st = 0; st < A; ++st) u[st] = v[st];
+                        lf_sadct_fwd(u, sh, ASW);
+#pragma unroll
+                        for (int st = 0; st < A; ++st) v[st] = u[st];
+                    } else lf_dct4_fwd<ASW>(v);
+#pragma unroll
+                    for (int st = 0; st < A; ++st) B[off + st * PS] = v[st];
+                }
+            }
+            __syncthreads();
+        }
+        // ---- 5th dimension + shrinkage (core:371-410 / :1170-1210) ----
+        float wpart = 0.f;
+        for (int t = tid; t < A * k2; t += nth) {
+            const int st = t >> (2 * g.log2k), pq = t & (k2 - 1);
+            const int base = st * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+            const bool shrink = !use_sadct || sh.mask_dct[st];
+            const int ns = A * PS;
+            switch (nSx) {
+                case 1:  wpart += lf_filter5d<STEP, 1>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+                case 2:  wpart += lf_filter5d<STEP, 2>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+                case 4:  wpart += lf_filter5d<STEP, 4>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+                case 8:  wpart += lf_filter5d<STEP, 8>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+                case 16: wpart += lf_filter5d<STEP, 16>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+                default: wpart += lf_filter5d<STEP, 32>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
+            }
+        }
+        const float wsum = lf_block_sum_f(wpart, red);     // also a barrier for the phase above
+        const float sg = c_tab.sigma[c];
+        const float wgt = wsum > 0.0f ? (sg > 0.0f ? 1.0f / (c_tab.sigma2[c] * wsum) : 1.0f / wsum) : 1.0f;   // core:419-420
+        float *Z = STEP == 1 ? X : E;
+        // ---- inverse angular transform (core:432-451) ----
+        if (g.tau_4D != 4) {
+            for (int t = tid; t < nSx * k2; t += nth) {
+                const int n = t >> (2 * g.log2k), pq = t & (k2 - 1);
+                const int off = n * A * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+                float v[A];
+#pragma unroll
+                for (int st = 0; st < A; ++st) v[st] = Z[off + st * PS];
+                if (use_sadct) {
+                    float u[A];
+#pragma unroll
+                    for (int st = 0; st < A; ++st) u[st] = v[st];
+                    lf_sadct_inv(u, sh, ASW);
+#pragma unroll
+                    for (int st = 0; st < A; ++st) v[st] = u[st];
+                } else lf_dct4_inv<ASW>(v);
+#pragma unroll
+                for (int st = 0; st < A; ++st) Z[off + st * PS] = v[st];
+            }
+            __syncthreads();
+        }
+        // ---- inverse 2-D transform (core:489-493) ----
+        lf_t2d(Z, npatch, g, false);
+        // ---- aggregation (core:496-526) ----
+        for (int t = tid; t < npatch * k2; t += nth) {
+            const int pa = t >> (2 * g.log2k), pq = t & (k2 - 1);
+            const int p = pq >> g.log2k, q = pq & (k - 1);
+            const int st = pa % A;
+            if (g.win.proc[st]) continue;
+            if (g.tau_4D == 6 && st != g.pst && !sh.mask[st]) continue;
+            const size_t dst = ((size_t) st * g.C + c) * plane + spos[pa] + (size_t) p * w + q;
+            const float kw = c_tab.kaiser[pq] * wgt;
+            atomicAdd(g.numsym + dst, kw * Z[pa * PS + p * RS + q]);
+            atomicAdd(g.densym + dst, kw);
+        }
+        __syncthreads();
+    }
+}

@@ -1,0 +1,738 @@
+// Host side of the C ABI (include/lfbm5d_cuda.h): device buffers, per-step constant tables, the window schedule of
+// the reference's step drivers (bm5d.cpp:165-407 / :861-1106, nb_threads == 1 semantics) and the per-pass kernel
+// sequence (bm5d_core_processing.cpp:90-530 / :859-1331, `pst == cst` branch).
+#include "lfbm5d_cuda.h"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "block_matching.cuh"
+#include "groups.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string &m) { g_err = m; return 1; }
+
+#define CK(x)                                                                                              \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(std::string(#x) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        cap = bytes;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+const double SQRT2_D = 1.414213562373095, SQRT2_INV_D = 0.7071067811865475;
+
+// utilities.cpp:697-712
+std::vector<int> ind_initialize(unsigned max_size, unsigned N, unsigned step)
+{
+    std::vector<int> v;
+    unsigned ind = N;
+    while (ind < max_size - N) { v.push_back((int) ind); ind += step; }
+    if (v.empty() || (unsigned) v.back() < max_size - N - 1) v.push_back((int) (max_size - N - 1));
+    return v;
+}
+
+// utilities.cpp:633-684
+int estimate_sigma(float sigma, float *t, unsigned chnls, unsigned cs)
+{
+    if (chnls == 1) { t[0] = sigma; return 0; }
+    if (cs == LFBM5D_YUV) {
+        t[0] = sqrtf(0.299f * 0.299f + 0.587f * 0.587f + 0.114f * 0.114f) * sigma;
+        t[1] = sqrtf(0.14713f * 0.14713f + 0.28886f * 0.28886f + 0.436f * 0.436f) * sigma;
+        t[2] = sqrtf(0.615f * 0.615f + 0.51498f * 0.51498f + 0.10001f * 0.10001f) * sigma;
+    } else if (cs == LFBM5D_YCBCR) {
+        t[0] = sqrtf(0.299f * 0.299f + 0.587f * 0.587f + 0.114f * 0.114f) * sigma;
+        t[1] = sqrtf(0.169f * 0.169f + 0.331f * 0.331f + 0.500f * 0.500f) * sigma;
+        t[2] = sqrtf(0.500f * 0.500f + 0.419f * 0.419f + 0.081f * 0.081f) * sigma;
+    } else if (cs == LFBM5D_OPP) {
+        t[0] = sqrtf(0.333f * 0.333f + 0.333f * 0.333f + 0.333f * 0.333f) * sigma;
+        t[1] = sqrtf(0.5f * 0.5f + 0.0f * 0.0f + 0.5f * 0.5f) * sigma;
+        t[2] = sqrtf(0.25f * 0.25f + 0.5f * 0.5f + 0.25f * 0.25f) * sigma;
+    } else if (cs == LFBM5D_RGB) {
+        t[0] = t[1] = t[2] = sigma;
+    } else return 1;
+    return 0;
+}
+
+// utilities_LF.cpp:881-901
+void angular_search_window(int &c_asw, int &min_asw, int &max_asw, unsigned aidx, unsigned asize, unsigned asize_sw)
+{
+    min_asw = (int) aidx - (int) asize_sw;
+    max_asw = (int) aidx + (int) asize_sw;
+    int shift = min_asw < 0 ? -min_asw : 0;
+    min_asw += shift; max_asw += shift;
+    c_asw = (int) asize_sw - shift;
+    shift = max_asw >= (int) asize ? ((int) asize - max_asw - 1) : 0;
+    min_asw += shift; max_asw += shift; c_asw -= shift;
+}
+
+void dct_tables(float *f, float *inv, int n)
+{
+    for (int kk = 0; kk < n; kk++)
+        for (int j = 0; j < n; j++) {
+            f[kk * n + j] = (float) (2.0 * cos(M_PI * ((double) j + 0.5) * (double) kk / (double) n));
+            inv[kk * n + j] = j == 0 ? 1.0f : (float) (2.0 * cos(M_PI * (double) j * ((double) kk + 0.5) / (double) n));
+        }
+}
+
+// everything a pass needs to know (padded geometry)
+struct PassCfg {
+    int step;
+    unsigned asw, A, C, W, H, n, nSim, nDisp, k, N, p, wb, hb;
+    unsigned tau_2D, tau_4D, tau_5D;
+    float tauMatch;
+    std::vector<int> rows, cols;
+};
+
+} // namespace
+
+struct lfbm5d_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    DevBuf noisy, basic, out, num, den, mask;
+    DevBuf nsym, bsym, numsym, densym, est0;
+    DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, descs, bnd, rowmap, colmap, rows, cols, counters;
+    lfbm5d_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev[4]{};
+    unsigned max_passes = 0;
+    std::vector<unsigned> sched;
+    bool geom_valid = false;
+    unsigned geom_key[8]{};
+};
+
+namespace {
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                          \
+    do {                                                                    \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);      \
+        (ctx)->stats.kernel_launches++;                                     \
+    } while (0)
+
+int grid_for(const lfbm5d_ctx *ctx, size_t n, int block = 256)
+{
+    size_t g = (n + block - 1) / block;
+    const size_t cap = (size_t) ctx->num_sms * 16;
+    return (int) std::max<size_t>(1, std::min(g, cap));
+}
+
+int validate(const lfbm5d_params *p, int step)
+{
+    if (!p) return fail("null params");
+    if (p->chnls != 1 && p->chnls != 3) return fail("chnls must be 1 or 3");
+    if (p->awidth == 0 || p->aheight == 0 || p->width == 0 || p->height == 0) return fail("empty light field");
+    const unsigned asw = 2 * p->an + 1;
+    if (asw > p->aheight || asw > p->awidth)   // bm5d.cpp:120-124
+        return fail("Wrong size of angular search window, the angular search window must be smaller than the light field angular size.");
+    if (asw > LF_MAXASW) return fail("angular half window > 1 is not supported by this build");
+    if (p->k != 8 && p->k != 16) return fail("patch size must be 8 or 16 in this build");
+    if (p->N == 0 || p->N > LF_MAXN || (p->N & (p->N - 1))) return fail("N must be a power of two <= 32");
+    if (p->nDisp > 6) return fail("nDisp > 6 is not supported by this build");
+    if (p->nSim + p->nDisp + 1 < p->k) return fail("nSim + nDisp must be >= k - 1");
+    if (p->p == 0) return fail("processing step must be >= 1");
+    if (p->tau_2D != LFBM5D_ID && p->tau_2D != LFBM5D_DCT && p->tau_2D != LFBM5D_BIOR) return fail("tau_2D must be id, dct or bior");
+    if (p->tau_4D != LFBM5D_ID && p->tau_4D != LFBM5D_DCT && p->tau_4D != LFBM5D_SADCT) return fail("tau_4D must be id, dct or sadct");
+    if (p->tau_5D != LFBM5D_HAAR && p->tau_5D != LFBM5D_HADAMARD) return fail("tau_5D must be haar or hw in this build (5-D dct: not yet)");
+    if (p->useSD) return fail("useSD weighting is not supported by this build");
+    if (p->ang_major != LFBM5D_ROWMAJOR && p->ang_major != LFBM5D_COLMAJOR) return fail("ang_major must be row or col");
+    if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");   // utilities.cpp:588-592
+    if (p->height < p->k || p->width < p->k) return fail("image smaller than a patch");
+    (void) step;
+    return 0;
+}
+
+int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau_4D)
+{
+    static LfTables T;    // host staging (pageable); copy is synchronous with respect to the host
+    memset(&T, 0, sizeof(T));
+    const int k = (int) p->k, asw = (int) (2 * p->an + 1);
+    dct_tables(T.dct2f, T.dct2i, k);
+    {   // bm3d.cpp:1101-1169
+        static const float k8[16] = { 0.1924f, 0.2989f, 0.3846f, 0.4325f, 0.2989f, 0.4642f, 0.5974f, 0.6717f,
+                                      0.3846f, 0.5974f, 0.7688f, 0.8644f, 0.4325f, 0.6717f, 0.8644f, 0.9718f };
+        if (k == 8) {
+            for (int i = 0; i < 8; i++)
+                for (int j = 0; j < 8; j++) T.kaiser[i * 8 + j] = k8[(i < 4 ? i : 7 - i) * 4 + (j < 4 ? j : 7 - j)];
+        } else
+            for (int i = 0; i < k * k; i++) T.kaiser[i] = 1.0f;
+        const float coef = 0.5f / ((float) k);
+        for (int i = 0; i < k; i++)
+            for (int j = 0; j < k; j++) {
+                if (i == 0 && j == 0) { T.cn2[i * k + j] = 0.5f * coef; T.cni2[i * k + j] = 2.0f; }
+                else if (i * j == 0) { T.cn2[i * k + j] = (float) (SQRT2_INV_D * coef); T.cni2[i * k + j] = (float) SQRT2_D; }
+                else { T.cn2[i * k + j] = 1.0f * coef; T.cni2[i * k + j] = 1.0f; }
+            }
+        T.coef2inv = 1.0f / (float) (k * 2);
+    }
+    for (int n = 1; n <= asw; n++) dct_tables(T.dctaf[n - 1], T.dctai[n - 1], n);
+    {   // core:3191-3216
+        const float coef = 0.5f / (sqrtf((float) asw) * sqrtf((float) asw));
+        for (int i = 0; i < asw; i++)
+            for (int j = 0; j < asw; j++) {
+                if (i == 0 && j == 0) { T.cn4[i * asw + j] = (float) (0.5f * coef); T.cni4[i * asw + j] = 2.0f; }
+                else if (i * j == 0) { T.cn4[i * asw + j] = (float) (SQRT2_INV_D * coef); T.cni4[i * asw + j] = (float) SQRT2_D; }
+                else { T.cn4[i * asw + j] = (float) (1.0f * coef); T.cni4[i * asw + j] = 1.0f; }
+            }
+        T.coef4inv = 1.0f / (sqrtf((float) asw) * sqrtf((float) asw) * 2.0f);   // core:1945
+    }
+    for (int n = 2; n <= asw; n++) {   // core:3229-3252
+        const float coef = (float) ((float) SQRT2_D / sqrt((double) n));
+        T.cnsa[n - 2][0] = (float) (SQRT2_INV_D * coef);
+        T.cnisa[n - 2][0] = (float) SQRT2_D;
+        for (int i = 1; i < n; i++) { T.cnsa[n - 2][i] = coef; T.cnisa[n - 2][i] = 1.0f; }
+    }
+    for (int n = 1; n <= asw; n++) T.coefsa_inv[n] = 0.5f * (float) (SQRT2_INV_D) / sqrtf((float) n);   // core:2190, :2242
+    {   // lib_transforms.cpp:215-277
+        const float coef_norm = 1.f / (sqrtf(2.f) * 128.f), sqrt2_inv = 1.f / sqrtf(2.f);
+        static const float a[10] = { 3.f, -3.f, -22.f, 22.f, 128.f, 128.f, 22.f, -22.f, -3.f, 3.f };
+        static const float d[10] = { 3.f, 3.f, -22.f, -22.f, 128.f, -128.f, 22.f, 22.f, -3.f, -3.f };
+        for (int i = 0; i < 10; i++) {
+            T.lpd[i] = a[i] * coef_norm;
+            T.hpr[i] = d[i] * coef_norm;
+            T.hpd[i] = i == 4 ? -sqrt2_inv : (i == 5 ? sqrt2_inv : 0.f);
+            T.lpr[i] = (i == 4 || i == 5) ? sqrt2_inv : 0.f;
+        }
+    }
+    if (estimate_sigma(p->sigma, T.sigma, p->chnls, p->color_space)) return fail("unknown colour space");
+    float lambda = p->lambda;
+    if (step == 1 && p->tau_2D == LFBM5D_ID && tau_4D == LFBM5D_DCT) lambda /= (float) (SQRT2_D);   // core:206-207
+    for (unsigned c = 0; c < p->chnls; c++) {
+        T.sigma2[c] = T.sigma[c] * T.sigma[c];
+        for (int lg = 0; lg < 8; lg++)   // core:2306 (hw) and :2431 (haar, lg = 0)
+            T.thr[c][lg] = lambda * T.sigma[c] * sqrtf((float) (1u << lg)) * (float) (SQRT2_D);
+    }
+    for (int lg = 0; lg < 8; lg++) T.hadcoef[lg] = 1.0f / (float) (1u << lg);
+    CK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int make_passcfg(PassCfg &pc, int step, const lfbm5d_params *p, unsigned tau_4D)
+{
+    pc.step = step;
+    pc.asw = 2 * p->an + 1; pc.A = pc.asw * pc.asw; pc.C = p->chnls; pc.W = p->width; pc.H = p->height;
+    pc.nSim = p->nSim; pc.nDisp = p->nDisp; pc.n = p->nSim + p->nDisp; pc.k = p->k; pc.N = p->N; pc.p = p->p;
+    pc.wb = pc.W + 2 * pc.n; pc.hb = pc.H + 2 * pc.n;
+    pc.tau_2D = p->tau_2D; pc.tau_4D = tau_4D; pc.tau_5D = p->tau_5D;
+    float st[3];
+    if (estimate_sigma(p->sigma, st, p->chnls, p->color_space)) return fail("unknown colour space");
+    pc.tauMatch = (p->chnls == 1 ? 3.f : 1.f) * (st[0] < 35.0f ? (step == 1 ? 3000 : 2000) : 5000);   // core:146 / :915
+    pc.rows = ind_initialize(pc.hb - pc.k + 1, pc.n, pc.p);
+    pc.cols = ind_initialize(pc.wb - pc.k + 1, pc.n, pc.p);
+    return 0;
+}
+
+// upload the reference-patch grid (once per step)
+int upload_grid(lfbm5d_ctx *ctx, const PassCfg &pc)
+{
+    std::vector<int> rowmap(pc.hb, -1), colmap(pc.wb, -1);
+    for (size_t a = 0; a < pc.rows.size(); a++) rowmap[pc.rows[a]] = (int) a;
+    for (size_t b = 0; b < pc.cols.size(); b++) colmap[pc.cols[b]] = (int) b;
+    if (ctx->rowmap.ensure(pc.hb * 4) || ctx->colmap.ensure(pc.wb * 4) || ctx->rows.ensure(pc.rows.size() * 4) ||
+        ctx->cols.ensure(pc.cols.size() * 4)) return 1;
+    CK(cudaMemcpyAsync(ctx->rowmap.p, rowmap.data(), pc.hb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->colmap.p, colmap.data(), pc.wb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rows.p, pc.rows.data(), pc.rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->cols.p, pc.cols.data(), pc.cols.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
+{
+    const size_t plane = (size_t) pc.wb * pc.hb, R = pc.rows.size() * pc.cols.size();
+    const size_t Ns = 2 * pc.nSim + 1, nself = (pc.nSim + 1) * Ns, Nd = 2 * pc.nDisp + 1;
+    if (ctx->nsym.ensure(pc.A * pc.C * plane * 4) || ctx->numsym.ensure(pc.A * pc.C * plane * 4) ||
+        ctx->densym.ensure(pc.A * pc.C * plane * 4) || ctx->est0.ensure(pc.A * plane * 4)) return 1;
+    if (pc.step == 2 && ctx->bsym.ensure(pc.A * pc.C * plane * 4)) return 1;
+    if (pc.N > 1 && (ctx->s_at.ensure(nself * R * 4) || ctx->s_mir.ensure(nself * R * 4))) return 1;
+    if (pc.A > 1 && ctx->sums.ensure((pc.A - 1) * Nd * Nd * plane * 4)) return 1;
+    if (ctx->first.ensure(pc.A * plane * 4) || ctx->shape.ensure(pc.A * plane)) return 1;
+    if (ctx->bmcount.ensure(R * 4) || ctx->bmidx.ensure(R * (pc.N + 1) * 4)) return 1;
+    const size_t nplanes = nself + (pc.A - 1) * Nd * Nd;
+    if (ctx->descs.ensure(nplanes * sizeof(SatDesc)) || ctx->bnd.ensure(nplanes * 2 * pc.hb * 4)) return 1;
+    if (ctx->counters.ensure(64 * 8)) return 1;
+    return 0;
+}
+
+__global__ void k_bm_identity(const int *rows, const int *cols, int nc, int w, int R, int N, unsigned *out_count, unsigned *out_idx)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    out_count[r] = 1;
+    out_idx[(size_t) r * (N + 1)] = (unsigned) (rows[r / nc] * w + cols[r % nc]);    // core:3448-3460
+}
+
+// One core call on the padded device buffers of the window (nsym/bsym/numsym/densym/est0 already filled).
+int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
+{
+    const size_t plane = (size_t) pc.wb * pc.hb;
+    const int nr = (int) pc.rows.size(), nc = (int) pc.cols.size(), R = nr * nc;
+    const int Ns = 2 * (int) pc.nSim + 1, nself = pc.N > 1 ? ((int) pc.nSim + 1) * Ns : 0;
+    const int Nd = 2 * (int) pc.nDisp + 1, nd2 = Nd * Nd;
+    const float threshold = pc.tauMatch * pc.k * pc.k;       // core:3315
+    const float *est0 = ctx->est0.as<float>();
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+
+    // ---- plane descriptors: self similarity first, then every other SAI of the window ----
+    std::vector<SatDesc> descs;
+    std::vector<int> stereo_sai;
+    for (int ddk = 0; ddk < nself; ddk++) {
+        const int di = ddk / Ns, djx = ddk % Ns;
+        SatDesc d{};
+        d.img1 = est0 + (size_t) pst * plane; d.img2 = d.img1;
+        d.dk = di * (int) pc.wb + djx - (int) pc.nSim;                 // core:3331
+        d.out_at = ctx->s_at.as<float>() + (size_t) ddk * R;
+        d.out_mir = ctx->s_mir.as<float>() + (size_t) ddk * R;
+        d.mir_di = di; d.mir_dc = (int) pc.nSim - djx;
+        d.bnd = ctx->bnd.as<float>() + (size_t) descs.size() * 2 * pc.hb;
+        descs.push_back(d);
+    }
+    int slot = 0;
+    for (int st = 0; st < (int) pc.A; st++) {
+        if (st == pst || !win.mask[st]) continue;
+        for (int ddk = 0; ddk < nd2; ddk++) {
+            const int di = ddk / Nd, dj = ddk % Nd;
+            SatDesc d{};
+            d.img1 = est0 + (size_t) pst * plane; d.img2 = est0 + (size_t) st * plane;
+            d.dk = di * (int) pc.wb + dj - (int) (pc.nDisp * (1 + pc.wb));   // core:3516
+            d.out_plane = ctx->sums.as<float>() + ((size_t) slot * nd2 + ddk) * plane;
+            d.bnd = ctx->bnd.as<float>() + (size_t) descs.size() * 2 * pc.hb;
+            descs.push_back(d);
+        }
+        stereo_sai.push_back(st);
+        slot++;
+    }
+    if (!descs.empty())
+        CK(cudaMemcpyAsync(ctx->descs.p, descs.data(), descs.size() * sizeof(SatDesc), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
+    if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
+    if (nself > 0) {
+        LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
+        SatGeom g{};
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n; g.dlo = pc.n;
+        g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
+        LAUNCH(ctx, k_sat_planes<true>, nself, 32, 0, g, ctx->descs.as<SatDesc>());
+    }
+    if (slot > 0) {
+        SatGeom g{};
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.nDisp; g.row_end = pc.hb - pc.nDisp - pc.k + 1;
+        g.col_end = pc.wb - pc.nDisp - pc.k + 1; g.dlo = pc.nDisp;
+        LAUNCH(ctx, k_sat_planes<false>, slot * nd2, 32, 0, g, ctx->descs.as<SatDesc>() + nself);
+    }
+    if (ctx->timing) CK(cudaEventRecord(sat1, ctx->stream));
+    // ---- selection ----
+    if (nself > 0) {
+        SelGeom sg{};
+        sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = Ns; sg.N = pc.N; sg.R = R; sg.nc = nc; sg.threshold = threshold;
+        sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
+        LAUNCH(ctx, k_bm_select, R, 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
+               ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+    } else {
+        LAUNCH(ctx, k_bm_identity, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) pc.wb, R, (int) pc.N,
+               ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+    }
+    for (int s = 0; s < slot; s++) {
+        const int st = stereo_sai[s];
+        const int row_end = pc.hb - pc.nDisp - pc.k + 1, col_end = pc.wb - pc.nDisp - pc.k + 1;
+        const size_t total = (size_t) (row_end - pc.nDisp) * (col_end - pc.nDisp);
+        LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, total, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * plane, (int) pc.wb,
+               (int) pc.hb, (int) pc.nDisp, row_end, col_end, threshold, ctx->first.as<unsigned>() + (size_t) st * plane,
+               ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned *) nullptr);
+    }
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    // ---- groups ----
+    GroupArgs ga{};
+    ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
+    ga.pst = pst; ga.nc = nc;
+    ga.RS = pc.tau_2D == LFBM5D_ID ? pc.k : pc.k + 1;
+    ga.PS = pc.k * ga.RS;
+    ga.tau_2D = pc.tau_2D; ga.tau_4D = pc.tau_4D; ga.tau_5D = pc.tau_5D;
+    ga.rows = ctx->rows.as<int>(); ga.cols = ctx->cols.as<int>();
+    ga.bm_count = ctx->bmcount.as<unsigned>(); ga.bm_idx = ctx->bmidx.as<unsigned>();
+    ga.first = ctx->first.as<unsigned>(); ga.shape = ctx->shape.as<unsigned char>();
+    ga.nsym = ctx->nsym.as<float>(); ga.bsym = ctx->bsym.as<float>();
+    ga.numsym = ctx->numsym.as<float>(); ga.densym = ctx->densym.as<float>();
+    ga.win = win;
+    const size_t smem = (size_t) pc.N * pc.A * ga.PS * 4 * (pc.step == 2 ? 2 : 1);
+    void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
+                                          : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
+    CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kfn<<<R, 256, smem, ctx->stream>>>(ga);
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    ctx->stats.window_passes++;
+    if (ctx->timing) {
+        cudaEvent_t e2;
+        CK(cudaEventCreate(&e2));
+        CK(cudaEventRecord(e2, ctx->stream));
+        CK(cudaEventSynchronize(e2));
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&b, ctx->ev[1], e2);
+        cudaEventElapsedTime(&c, sat0, sat1);
+        ctx->stats.ms_block_matching += a; ctx->stats.ms_groups += b; ctx->stats.ms_sat += c;
+        cudaEventDestroy(e2);
+    }
+    return 0;
+}
+
+// The reference's step driver for nb_threads == 1 (bm5d.cpp:165-407 / :861-1106) on device-resident light fields.
+int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy, float *d_basic, float *d_out, const unsigned *mask)
+{
+    if (validate(p, step)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
+    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    const size_t HW = (size_t) W * H, each = HW * C;
+    ctx->sched.clear();
+    cudaEvent_t e_begin = nullptr, e_end = nullptr;
+    if (ctx->timing) { CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end)); CK(cudaEventRecord(e_begin, ctx->stream)); }
+    const float bm0 = ctx->stats.ms_block_matching, gr0 = ctx->stats.ms_groups;
+
+    // a window containing an empty SAI turns dct into sadct for the rest of the step (bm5d.cpp:276-280)
+    unsigned tau_4D = p->tau_4D;
+    std::vector<unsigned> proc(asize);
+    unsigned remaining = 0;
+    for (unsigned st = 0; st < asize; st++) { proc[st] = !mask[st]; remaining += proc[st] == 0; }
+    const unsigned max_proc = remaining;
+
+    if (ctx->mask.ensure(asize * 4) || ctx->num.ensure(asize * each * 4) || ctx->den.ensure(asize * each * 4)) return 1;
+    CK(cudaMemcpyAsync(ctx->mask.p, mask, asize * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const bool docolor = C == 3 && p->color_space != LFBM5D_RGB;
+    if (docolor) {
+        LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_noisy, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
+        if (step == 2) LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_basic, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
+    }
+    CK(cudaMemsetAsync(ctx->num.p, 0, asize * each * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
+
+    PassCfg pc;
+    if (make_passcfg(pc, step, p, tau_4D)) return 1;
+    if (setup_tables(ctx, step, p, tau_4D)) return 1;
+    if (ensure_pass_buffers(ctx, pc) || upload_grid(ctx, pc)) return 1;
+    unsigned tables_tau4 = tau_4D;
+
+    std::vector<char> touched(asize, 0);
+    unsigned passes = 0;
+    unsigned long long *counters = ctx->counters.as<unsigned long long>();
+    while (remaining) {
+        unsigned ps, pt, pst_g = 0;
+        if (remaining == max_proc && mask[cst]) { ps = cs; pt = ct; }
+        else {   // bm5d.cpp:189-202: most entries still at 0, ties to the highest index
+            long long best = -1;
+            std::vector<unsigned> need;
+            for (unsigned st = 0; st < asize; st++) if (!proc[st] && touched[st]) need.push_back(st);
+            std::vector<unsigned long long> zc(asize, (unsigned long long) each);
+            if (!need.empty()) {
+                if (ctx->counters.ensure((need.size() + 8) * 8)) return 1;
+                counters = ctx->counters.as<unsigned long long>();
+                CK(cudaMemsetAsync(counters, 0, need.size() * 8, ctx->stream));
+                for (size_t i = 0; i < need.size(); i++)
+                    LAUNCH(ctx, k_count_zero, grid_for(ctx, each), 256, 0, ctx->den.as<float>() + need[i] * each, each, counters + i);
+                std::vector<unsigned long long> h(need.size());
+                CK(cudaMemcpyAsync(h.data(), counters, need.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                for (size_t i = 0; i < need.size(); i++) zc[need[i]] = h[i];
+            }
+            for (unsigned st = 0; st < asize; st++) {
+                if (proc[st]) continue;
+                const long long z = (long long) (int) zc[st];     // the reference keeps the count in an int
+                if (z >= best) { pst_g = st; best = z; }
+            }
+            if (p->ang_major == LFBM5D_ROWMAJOR) { ps = pst_g / p->awidth; pt = pst_g - ps * p->awidth; }
+            else { pt = pst_g / p->aheight; ps = pst_g - pt * p->aheight; }
+        }
+        int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
+        angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
+        angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
+        const unsigned cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
+        LfWindow win{};
+        win.A = (int) Aw;
+        unsigned n_unproc = 0;
+        for (unsigned s_a = 0; s_a < asw; s_a++)
+            for (unsigned t_a = 0; t_a < asw; t_a++) {
+                const unsigned s = s_a + min_s, t = t_a + min_t;
+                unsigned st, a;
+                if (p->ang_major == LFBM5D_ROWMAJOR) { st = s * p->awidth + t; a = s_a * asw + t_a; }
+                else { st = s + t * p->aheight; a = s_a + t_a * asw; }
+                win.st[a] = (int) st;
+                win.mask[a] = mask[st];
+                win.proc[a] = !mask[st];
+                n_unproc += mask[st] != 0;
+            }
+        if (n_unproc != Aw && tau_4D == LFBM5D_DCT) tau_4D = LFBM5D_SADCT;
+        if (tau_4D != tables_tau4) {
+            pc.tau_4D = tau_4D;
+            if (setup_tables(ctx, step, p, tau_4D)) return 1;
+            tables_tau4 = tau_4D;
+        }
+        LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) Aw * pc.wb * pc.hb), 256, 0, d_noisy, step == 2 ? d_basic : (const float *) nullptr,
+               ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
+               ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
+        const unsigned max_unproc = n_unproc;
+        unsigned calls = 0;
+        while (n_unproc) {
+            unsigned pst_asw;
+            if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
+            else return fail("window not covered after its first SAI: the `pst != cst` partial-window path "
+                             "(bm5d_core_processing.cpp:531-821) is not implemented in this build");
+            if (run_pass(ctx, pc, win, (int) pst_asw)) return 1;
+            calls++;
+            win.proc[pst_asw] += 1;
+            proc[win.st[pst_asw]] += 1;
+            // LF_denoised_percent (utilities_LF.cpp:967-995): float counter (saturates at 2^24), normalised without C
+            CK(cudaMemsetAsync(counters, 0, 8, ctx->stream));
+            LAUNCH(ctx, k_count_denoised, grid_for(ctx, (size_t) Aw * C * (H - pc.k + 1) * (W - pc.k + 1)), 256, 0, ctx->densym.as<float>(),
+                   win, (int) W, (int) H, (int) C, (int) pc.n, (int) pc.k, counters);
+            unsigned long long cnt = 0;
+            CK(cudaMemcpyAsync(&cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const float fcnt = (float) std::min<unsigned long long>(cnt, 16777216ull);
+            unsigned nmask = 0;
+            for (unsigned a = 0; a < Aw; a++) nmask += win.mask[a] == 1;
+            const float pct = fcnt * 100.0f / (float) nmask / (float) (H - pc.k + 1) / (float) (W - pc.k + 1);
+            if (pct >= 100.0f)
+                for (unsigned a = 0; a < Aw; a++)
+                    if (win.proc[a] == 0) { win.proc[a] += 1; proc[win.st[a]] += 1; }
+            n_unproc = 0;
+            for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
+        }
+        LAUNCH(ctx, k_unpad_window, grid_for(ctx, (size_t) Aw * each), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
+               ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
+        for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) touched[win.st[a]] = 1;
+        ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
+        ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
+        remaining = 0;
+        for (unsigned st = 0; st < asize; st++) remaining += proc[st] == 0;
+        passes++;
+        if (ctx->max_passes && passes >= ctx->max_passes) break;
+    }
+    LAUNCH(ctx, k_final, grid_for(ctx, asize * HW), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), d_noisy, d_basic, d_out,
+           ctx->mask.as<unsigned>(), asize, HW, (int) C, step, p->color_space, docolor ? 1 : 0);
+    CK(cudaGetLastError());
+    if (ctx->timing) {
+        CK(cudaEventRecord(e_end, ctx->stream));
+        CK(cudaEventSynchronize(e_end));
+        float total = 0;
+        cudaEventElapsedTime(&total, e_begin, e_end);
+        ctx->stats.ms_other += total - (ctx->stats.ms_block_matching - bm0) - (ctx->stats.ms_groups - gr0);
+        cudaEventDestroy(e_begin); cudaEventDestroy(e_end);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int upload_lf(lfbm5d_ctx *ctx, DevBuf &buf, float *const *host, const unsigned *mask, unsigned asize, size_t each)
+{
+    if (buf.ensure(asize * each * 4)) return 1;
+    for (unsigned st = 0; st < asize; st++)
+        if (mask[st]) CK(cudaMemcpyAsync(buf.as<float>() + st * each, host[st], each * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+int download_lf(lfbm5d_ctx *ctx, const DevBuf &buf, float *const *host, const unsigned *mask, unsigned asize, size_t each)
+{
+    for (unsigned st = 0; st < asize; st++)
+        if (mask[st]) CK(cudaMemcpyAsync(host[st], buf.as<float>() + st * each, each * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *lfbm5d_last_error(void) { return g_err.c_str(); }
+
+int lfbm5d_create(lfbm5d_ctx **out, int device)
+{
+    if (!out) return fail("null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("invalid device index");
+    CK(cudaSetDevice(device));
+    lfbm5d_ctx *ctx = new lfbm5d_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
+    *out = ctx;
+    return 0;
+}
+
+void lfbm5d_destroy(lfbm5d_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
+                      &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
+                      &ctx->bmidx, &ctx->descs, &ctx->bnd, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters };
+    for (auto b : all) b->release();
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void lfbm5d_reset_stats(lfbm5d_ctx *ctx) { if (ctx) ctx->stats = lfbm5d_stats{}; }
+void lfbm5d_get_stats(lfbm5d_ctx *ctx, lfbm5d_stats *out) { if (ctx && out) *out = ctx->stats; }
+void lfbm5d_enable_timing(lfbm5d_ctx *ctx, int on) { if (ctx) ctx->timing = on != 0; }
+void *lfbm5d_stream(lfbm5d_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned m) { if (ctx) ctx->max_passes = m; }
+
+int lfbm5d_step1_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, const unsigned *sai_mask, float *d_basic_out)
+{
+    if (!ctx || !d_noisy_io || !sai_mask || !d_basic_out) return fail("null argument");
+    return step_device(ctx, 1, p, d_noisy_io, nullptr, d_basic_out, sai_mask);
+}
+int lfbm5d_step2_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io, const unsigned *sai_mask,
+                        float *d_denoised_out)
+{
+    if (!ctx || !d_noisy_io || !d_basic_io || !sai_mask || !d_denoised_out) return fail("null argument");
+    return step_device(ctx, 2, p, d_noisy_io, d_basic_io, d_denoised_out, sai_mask);
+}
+
+int lfbm5d_step1(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out)
+{
+    if (!ctx || !noisy_io || !sai_mask || !basic_out) return fail("null argument");
+    if (validate(p, 1)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned asize = p->awidth * p->aheight;
+    const size_t each = (size_t) p->width * p->height * p->chnls;
+    if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || ctx->out.ensure(asize * each * 4)) return 1;
+    if (step_device(ctx, 1, p, ctx->noisy.as<float>(), nullptr, ctx->out.as<float>(), sai_mask)) return 1;
+    if (download_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each)) return 1;
+    return download_lf(ctx, ctx->out, basic_out, sai_mask, asize, each);
+}
+
+int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, float *const *basic_io, const unsigned *sai_mask,
+                 float *const *denoised_out)
+{
+    if (!ctx || !noisy_io || !basic_io || !sai_mask || !denoised_out) return fail("null argument");
+    if (validate(p, 2)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned asize = p->awidth * p->aheight;
+    const size_t each = (size_t) p->width * p->height * p->chnls;
+    if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || upload_lf(ctx, ctx->basic, basic_io, sai_mask, asize, each) ||
+        ctx->out.ensure(asize * each * 4)) return 1;
+    if (step_device(ctx, 2, p, ctx->noisy.as<float>(), ctx->basic.as<float>(), ctx->out.as<float>(), sai_mask)) return 1;
+    if (download_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || download_lf(ctx, ctx->basic, basic_io, sai_mask, asize, each)) return 1;
+    return download_lf(ctx, ctx->out, denoised_out, sai_mask, asize, each);
+}
+
+int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out,
+               float *const *denoised_out)
+{
+    (void) ctx; (void) p; (void) noisy_io; (void) sai_mask; (void) basic_out; (void) denoised_out;
+    return fail("lfbm3d_run: the per-SAI BM3D path is not implemented in this build");
+}
+
+unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries)
+{
+    if (!ctx) return 0;
+    const unsigned n = (unsigned) (ctx->sched.size() / 4);
+    for (unsigned i = 0; i < n && i < max_entries; i++)
+        for (int j = 0; j < 4; j++) out[4 * i + j] = ctx->sched[4 * i + j];
+    return n;
+}
+
+int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
+                      float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned pst,
+                      unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape)
+{
+    if (!ctx || !noisy_sym || !num_sym_io || !den_sym_io || !mask_asw || !procSAI_asw) return fail("null argument");
+    if (step != 1 && step != 2) return fail("step must be 1 or 2");
+    if (step == 2 && !basic_sym) return fail("step 2 needs the basic estimate");
+    lfbm5d_params q = *p;
+    if (q.awidth < 2 * q.an + 1) q.awidth = 2 * q.an + 1;
+    if (q.aheight < 2 * q.an + 1) q.aheight = 2 * q.an + 1;
+    if (validate(&q, step)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    PassCfg pc;
+    if (make_passcfg(pc, step, p, p->tau_4D) || setup_tables(ctx, step, p, p->tau_4D) || ensure_pass_buffers(ctx, pc) || upload_grid(ctx, pc))
+        return 1;
+    if (pst >= pc.A) return fail("pst out of range");
+    const size_t plane = (size_t) pc.wb * pc.hb, bytes = pc.A * pc.C * plane * 4;
+    LfWindow win{};
+    win.A = (int) pc.A;
+    for (unsigned a = 0; a < pc.A; a++) { win.st[a] = (int) a; win.mask[a] = mask_asw[a]; win.proc[a] = procSAI_asw[a]; }
+    CK(cudaMemcpyAsync(ctx->nsym.p, noisy_sym, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (step == 2) CK(cudaMemcpyAsync(ctx->bsym.p, basic_sym, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->numsym.p, num_sym_io, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->densym.p, den_sym_io, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->first.p, 0xFF, pc.A * plane * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->shape.p, 0, pc.A * plane, ctx->stream));
+    LAUNCH(ctx, k_est0, grid_for(ctx, pc.A * plane), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
+           ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, plane, (int) pc.C);
+    if (run_pass(ctx, pc, win, (int) pst)) return 1;
+    CK(cudaMemcpyAsync(num_sym_io, ctx->numsym.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(den_sym_io, ctx->densym.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t R = pc.rows.size() * pc.cols.size(), nc = pc.cols.size();
+    if (out_count && out_idx) {
+        std::vector<unsigned> cnt(R), idx(R * (pc.N + 1));
+        CK(cudaMemcpy(cnt.data(), ctx->bmcount.p, R * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(idx.data(), ctx->bmidx.p, R * (pc.N + 1) * 4, cudaMemcpyDeviceToHost));
+        memset(out_count, 0, plane * 4);
+        for (size_t r = 0; r < R; r++) {
+            const size_t k_r = (size_t) pc.rows[r / nc] * pc.wb + pc.cols[r % nc];
+            out_count[k_r] = cnt[r];
+            for (unsigned n = 0; n < cnt[r]; n++) out_idx[k_r * (pc.N + 1) + n] = idx[r * (pc.N + 1) + n];
+        }
+    }
+    if (out_first) CK(cudaMemcpy(out_first, ctx->first.p, pc.A * plane * 4, cudaMemcpyDeviceToHost));
+    if (out_shape) {
+        std::vector<unsigned char> s(pc.A * plane);
+        CK(cudaMemcpy(s.data(), ctx->shape.p, pc.A * plane, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < s.size(); i++) out_shape[i] = s[i];
+    }
+    return 0;
+}
+
+int lfbm5d_debug_bm_self(lfbm5d_ctx *ctx, const float *img, unsigned w_b, unsigned h_b, unsigned k, unsigned N, unsigned nHW,
+                         unsigned nSim, unsigned p, float tauMatch, unsigned *out_count, unsigned *out_idx)
+{
+    (void) ctx; (void) img; (void) w_b; (void) h_b; (void) k; (void) N; (void) nHW; (void) nSim; (void) p; (void) tauMatch;
+    (void) out_count; (void) out_idx;
+    return fail("use lfbm5d_debug_pass (it exports the match lists)");
+}
+int lfbm5d_debug_bm_stereo(lfbm5d_ctx *ctx, const float *img1, const float *img2, unsigned w_b, unsigned h_b, unsigned k,
+                           unsigned nHW, unsigned nDisp, float tauMatch, unsigned *out_first, unsigned *out_shape)
+{
+    (void) ctx; (void) img1; (void) img2; (void) w_b; (void) h_b; (void) k; (void) nHW; (void) nDisp; (void) tauMatch;
+    (void) out_first; (void) out_shape;
+    return fail("use lfbm5d_debug_pass (it exports the disparity matches)");
+}
+
+} // extern "C"
