@@ -58,7 +58,8 @@ typedef struct lfbm5d_stats {
     unsigned long long kernel_launches;   /* kernels of this library launched since the last reset */
     unsigned           window_passes;     /* core calls (bm5d_{1st,2nd}_step equivalents) since the last reset */
     float              ms_block_matching; /* device time (CUDA events) since the last reset, when timing is enabled */
-    float              ms_groups;         /* gather + transforms + shrinkage + aggregation */
+    float              ms_groups;         /* gather + transforms + shrinkage (+ staging of the filtered patches) */
+    float              ms_aggregate;      /* ordered weighted aggregation */
     float              ms_other;
     float              ms_sat;            /* summed-area kernel alone (dominant block-matching kernel) */
 } lfbm5d_stats;

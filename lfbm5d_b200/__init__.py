@@ -29,7 +29,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("window_passes", C.c_uint), ("ms_block_matching", C.c_float),
-                ("ms_groups", C.c_float), ("ms_other", C.c_float), ("ms_sat", C.c_float)]
+                ("ms_groups", C.c_float), ("ms_aggregate", C.c_float), ("ms_other", C.c_float), ("ms_sat", C.c_float)]
 
 
 EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset_stats", "lfbm5d_get_stats",

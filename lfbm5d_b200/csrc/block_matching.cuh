@@ -10,160 +10,252 @@
 #pragma once
 #include "common.cuh"
 
-struct SatDesc {
-    const float *img1;      // reference image (channel 0 of the running estimate)
-    const float *img2;      // image the offset is applied to
-    int          dk;        // flat offset: d(y,x) = (img2[y*w+x+dk] - img1[y*w+x])^2
-    float       *out_plane; // stereo: full plane of sums [h*w] (written on the computed region only)
-    float       *out_at;    // self: sums sampled at the reference patches, [nr*nc]
-    float       *out_mir;   // self: sums sampled at (ref - (mir_di, -mir_dc)), [nr*nc] (pre-filled with 2*threshold)
-    int          mir_di, mir_dc;
-    float       *bnd;       // scratch, 2*h floats: last column of the previous / current 32-column strip
-};
-
+// ---- geometry shared by all planes of one launch ----
 struct SatGeom {
     int w, h, k;
     int lo;                 // first row/column of the summed region
     int row_end, col_end;   // one past its last row/column
-    int dlo;                // squared differences are non-zero only on [dlo, h-dlo) x [dlo, w-dlo)
+    int ylim, xlim;         // squared differences are zero for rows >= ylim or columns >= xlim (self: dim - nHW)
+    int nstrips;            // 32-column strips
+    int SR;                 // skewed rows per strip in the stereo output: (row_end - lo) + 31
     int nc;                 // number of reference-patch columns (self)
     const int *rowmap;      // [h] row -> reference row index or -1 (self)
     const int *colmap;      // [w]
 };
+// One offset plane: d(y,x) = (img2[y+oy][x+ox] - img1[y][x])^2, oy shared by the group.
+struct SatPlane {
+    int    ox;
+    float *out_skew;        // stereo: sums in skewed layout [strip][sidx][lane], sidx = (i - lo) + lane
+    float *out_at;          // self: sums sampled at the reference patches, [nr*nc]
+    float *out_mir;         // self: sums sampled at (ref - (mir_di, -mir_dc)) (pre-filled with 2*threshold)
+    int    mir_di, mir_dc;
+};
+// Up to SAT_NW planes that share the two source images and the row offset: one CTA per (group, strip).
+#define SAT_NW 13
+struct SatGroup {
+    const float *img1, *img2;
+    int oy, oxmin, nplanes, first_plane;
+};
 
-// One warp per offset plane. The plane is swept in 32-column strips; inside a strip lane l owns column c0+l and
-// runs one row behind lane l-1, so that s(i, j-1) arrives by one shuffle per step. Squared differences are
-// produced one image row per step with coalesced loads into a 64-row shared-memory ring whose row stride (64
-// floats) makes the skewed reads bank-conflict free; finished rows are transposed through a 32x32 tile so that
-// results leave with coalesced 128-byte stores.
-template <bool SELF>
-__global__ void __launch_bounds__(32) k_sat_planes(SatGeom g, const SatDesc *__restrict__ descs)
+__device__ __forceinline__ void lf_cp_async4(float *smem_dst, const float *gsrc)
 {
-    __shared__ float dring[64 * 64];
-    __shared__ float tile[32 * 32];
-    __shared__ float frow[32];
-    const SatDesc D = descs[blockIdx.x];
-    const int lane = threadIdx.x;
-    const int w = g.w, k = g.k, lo = g.lo;
-    const int W = g.col_end - lo, Hh = g.row_end - lo;
-    const int nstrips = (W + 31) >> 5;
-    float *bnd_prev = D.bnd, *bnd_next = D.bnd + g.h;
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void lf_cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Summed-area planes, v2. Work unit = (group of <= 13 planes sharing their source rows, 32-column strip): one warp
+// per plane; lane l owns column c0+l and runs one row behind lane l-1 (skewed wavefront, one shuffle per step).
+// The strips of a plane are pipelined across CTAs: strip c consumes the last column of strip c-1 through global
+// memory with a per-(plane, strip) progress flag, and CTAs take their work from a ticket counter in strip-major
+// order so that a producer has always started before its consumer (no deadlock). Source rows of both images are
+// staged once per CTA with cp.async into two 128-row shared-memory rings (row stride 64 floats: the skewed reads
+// are bank-conflict free) and reused by all planes of the group; squared differences are formed on the fly.
+template <bool SELF, int K>
+__global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
+                                                          int ngroups, float *bnd, int *progress, int *ticket_counter)
+{
+    extern __shared__ float s_dyn[];
+    float *R1 = s_dyn, *R2 = s_dyn + 128 * 64;          // source-row rings of img1 / img2
+    int *s_maps = reinterpret_cast<int *>(s_dyn + 2 * 128 * 64);   // SELF: rowmap[h] then colmap[w]
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
+    if (tid == 0) s_ticket = atomicAdd(ticket_counter, 1);
+    if (SELF) {
+        for (int t = tid; t < g.h; t += blockDim.x) s_maps[t] = g.rowmap[t];
+        for (int t = tid; t < g.w; t += blockDim.x) s_maps[g.h + t] = g.colmap[t];
+    }
+    __syncthreads();
+    const int strip = s_ticket / ngroups, gi = s_ticket - strip * ngroups;
+    const SatGroup G = groups[gi];
+    const bool hasplane = warp < G.nplanes;
+    const int pid = G.first_plane + (hasplane ? warp : 0);
+    const SatPlane P = planes[pid];
+    const int w = g.w, h = g.h, lo = g.lo;
+    constexpr int k = K;
+    const int W = g.col_end - lo, Hh = g.row_end - lo;
+    const int c0 = lo + (strip << 5);
+    const int j = c0 + lane;
+    const bool valid = hasplane && j < g.col_end;
+    const int lastlane = min(31, W - 1 - (strip << 5));
+    const bool has_next = strip + 1 < g.nstrips;
+    const int xb1 = c0 - 1, xb2 = c0 - 1 + G.oxmin;
+    const int oxo = P.ox - G.oxmin;                    // column shift of this plane inside the img2 ring
+    const int ymax = min(g.row_end - 1 + k - 1, h - 1);   // last source row ever needed
+    float *bnd_prev = bnd + ((size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0)) * h;
+    float *bnd_next = bnd + ((size_t) pid * g.nstrips + strip) * h;
+    volatile int *prog_prev = progress + (size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0);
+    volatile int *prog_next = progress + (size_t) pid * g.nstrips + strip;
 
-    for (int strip = 0; strip < nstrips; ++strip) {
-        const int c0 = lo + (strip << 5);
-        const int j = c0 + lane;
-        const bool valid = j < g.col_end;
-        const int lastlane = min(31, W - 1 - (strip << 5));
-        const bool has_next = strip + 1 < nstrips;
-
-        auto load_drow = [&](int y) {
-            for (int t = lane; t < 32 + k; t += 32) {
-                const int x = c0 - 1 + t;
-                float v = 0.f;
-                if (y >= g.dlo && y < g.h - g.dlo && x >= g.dlo && x < w - g.dlo) {
-                    const float df = D.img2[y * w + x + D.dk] - D.img1[y * w + x];
-                    v = df * df;
-                }
-                dring[(y & 63) * 64 + t] = v;
-            }
-        };
-        auto emit_row = [&](int i, float v) {   // v = s(i, j) of this lane
-            if (SELF) {
-                if (!valid) return;
-                const int a = g.rowmap[i];
-                if (a >= 0) {
-                    const int b = g.colmap[j];
-                    if (b >= 0) D.out_at[a * g.nc + b] = v;
-                }
-                if (D.mir_di > 0) {
-                    const int ir = i + D.mir_di, jr = j - D.mir_dc;
-                    if (ir < g.h && jr >= 0 && jr < w) {
-                        const int a2 = g.rowmap[ir], b2 = g.colmap[jr];
-                        if (a2 >= 0 && b2 >= 0) D.out_mir[a2 * g.nc + b2] = v;
-                    }
-                }
+    // rows [y0, y1] of both images into the rings (all threads)
+    auto load_rows = [&](int y0, int y1) {
+        if (y1 > ymax) y1 = ymax;
+        const int n = (y1 - y0 + 1) * 128;
+        for (int t = tid; t < n; t += blockDim.x) {
+            const int y = y0 + (t >> 7), c = t & 63, which = (t >> 6) & 1;
+            if (which == 0) {
+                const int x = xb1 + c;
+                float *dst = &R1[(y & 127) * 64 + c];
+                if (x < w) lf_cp_async4(dst, G.img1 + (size_t) y * w + x); else *dst = 0.f;
             } else {
-                if (valid) D.out_plane[i * w + j] = v;
-            }
-        };
-
-        // ---- first row of the strip (core:3345-3362 / :3530-3547) ----
-        for (int y = lo; y < lo + k; ++y) load_drow(y);
-        __syncwarp();
-        for (int p = 0; p < k; ++p)
-            tile[p * 32 + lane] = dring[((lo + p) & 63) * 64 + lane + k] - dring[((lo + p) & 63) * 64 + lane];
-        __syncwarp();
-        if (lane == 0) {
-            float left;
-            int l0 = 0;
-            if (strip == 0) {
-                float v = 0.0f;
-                for (int p = 0; p < k; ++p)
-                    for (int q = 0; q < k; ++q) v += dring[((lo + p) & 63) * 64 + 1 + q];
-                frow[0] = v; left = v; l0 = 1;
-            } else left = __ldcg(&bnd_prev[lo]);
-            for (int l = l0; l <= lastlane; ++l) {
-                float s = left;
-                for (int p = 0; p < k; ++p) s += tile[p * 32 + l];
-                frow[l] = s; left = s;
+                const int yy = y + G.oy, x = xb2 + c;
+                float *dst = &R2[(yy & 127) * 64 + c];
+                if (yy >= 0 && yy < h && x >= 0 && x < w) lf_cp_async4(dst, G.img2 + (size_t) yy * w + x); else *dst = 0.f;
             }
         }
+    };
+    // squared difference at source row y, ring column slot cs (= x - xb1) — prologue / first-column paths only
+    auto dval = [&](int y, int cs) -> float {
+        const float a = R1[(y & 127) * 64 + cs];
+        const float b = R2[((y + G.oy) & 127) * 64 + cs + oxo];
+        const float df = b - a;
+        float v = df * df;
+        if (SELF) { if (y >= g.ylim || xb1 + cs >= g.xlim) v = 0.f; }
+        return v;
+    };
+    // per-lane constants of the sampled outputs (self) / the skewed output pointer (stereo)
+    int colb = -1, colb2 = -1;
+    float *outp = nullptr;
+    if (SELF) {
+        if (j < w) colb = s_maps[h + j];
+        const int jr = j - P.mir_dc;
+        if (P.mir_di > 0 && jr >= 0 && jr < w) colb2 = s_maps[h + jr];
+    } else {
+        outp = P.out_skew + ((size_t) strip * g.SR) * 32 + lane;      // + sidx*32, sidx = (i - lo) + lane
+    }
+    auto emit = [&](int i, float v) {     // s(i, j) of this lane
+        if (SELF) {
+            const int a = s_maps[i];
+            if (a >= 0 && colb >= 0) P.out_at[a * g.nc + colb] = v;
+            if (colb2 >= 0) {
+                const int a2 = s_maps[i + P.mir_di];
+                if (a2 >= 0) P.out_mir[a2 * g.nc + colb2] = v;
+            }
+        } else {
+            outp[(size_t) ((i - lo) + lane) * 32] = v;
+        }
+    };
+    auto wait_prev = [&](int need) {      // producer strip has published rows <= need (flag holds row + 1)
+        if (lane == 0) {
+            while (*prog_prev < need + 1) __nanosleep(100);
+            __threadfence();
+        }
         __syncwarp();
-        float cur = valid ? frow[lane] : 0.f;
-        float prevL;
+    };
+
+    // ---- prologue: rows for the first-row formulas and for chunk 0 ----
+    load_rows(lo, lo + 32 + k - 1);
+    lf_cp_async_wait_all();
+    __syncthreads();
+
+    float cur = 0.f, prevL = 0.f;
+    if (hasplane) {
+        // first row of the strip (core:3345-3362 / :3530-3547): s(lo, j) = s(lo, j-1) + sum_p (d[lo+p][j-1+k] - d[lo+p][j-1]),
+        // the differences formed in parallel (lane p), the additions strictly in order
+        float left = 0.f;
+        int l0 = 0;
+        if (strip == 0) {      // first patch: sequential sum over its k*k squared differences
+            float v = 0.0f;
+            for (int p = 0; p < k; ++p) {
+                const float dv = lane < k ? dval(lo + p, 1 + lane) : 0.f;
+                for (int t = 0; t < k; ++t) v += __shfl_sync(FULL, dv, t);
+            }
+            left = v; l0 = 1;
+            if (lane == 0) cur = v;
+        } else {
+            wait_prev(lo);
+            left = __ldcg(&bnd_prev[lo]);
+            prevL = left;       // lane 0: s(lo, c0-1)
+        }
+        for (int l = l0; l <= lastlane; ++l) {
+            float s = left;
+            const float e = lane < k ? dval(lo + lane, l + k) - dval(lo + lane, l) : 0.f;
+            for (int t = 0; t < k; ++t) s += __shfl_sync(FULL, e, t);
+            if (lane == l) cur = s;
+            left = s;
+        }
         {
             const float up = __shfl_up_sync(FULL, cur, 1);
-            prevL = lane == 0 ? (strip == 0 ? 0.f : __ldcg(&bnd_prev[lo])) : up;
+            if (lane > 0) prevL = up;
         }
-        emit_row(lo, cur);
-        if (has_next && lane == 31) __stcg(&bnd_next[lo], cur);
-        __syncwarp();
+        if (valid) emit(lo, cur);
+        if (has_next && lane == 31) { __stcg(&bnd_next[lo], cur); __threadfence(); *prog_next = lo + 1; }
+    }
 
-        // ---- wavefront over the remaining rows (core:3365-3387 / :3550-3572) ----
-        const int nsteps = (Hh - 1) + 31;
-        float bchunk = 0.f;
-        for (int s = 1; s <= nsteps; ++s) {
-            const int i0 = lo + s;
-            if (i0 < g.row_end) load_drow(i0 + k - 1);
-            if (strip > 0 && ((s - 1) & 31) == 0) {
-                const int r = i0 + lane;
+    // ---- wavefront over the remaining rows in chunks of 32 steps (core:3365-3387 / :3550-3572) ----
+    // Ring offsets of this lane (floats): row i+k-1 -> o1 (img1) / p1 (img2), row i-1 -> (o1 - 64k) & 8191; both advance
+    // by one ring row per step.
+    const int nsteps = (Hh - 1) + 31;
+    const int nchunks = (nsteps + 31) >> 5;
+    int o1 = ((lo + 1 - lane + k - 1) & 127) * 64;
+    int p1 = ((lo + 1 - lane + k - 1 + G.oy) & 127) * 64;
+    const float *r1a = R1 + lane, *r2a = R2 + lane + oxo;
+    const bool colz = SELF && (j + k - 1 >= g.xlim);
+    const bool skip0 = strip == 0 && lane == 0;
+    for (int q = 0; q < nchunks; ++q) {
+        // stage the source rows of the next chunk while this one runs
+        load_rows(lo + 32 * (q + 1) + k, lo + 32 * (q + 1) + 32 + k - 1);
+        if (hasplane) {
+            float bchunk = 0.f;
+            if (strip > 0) {
+                const int rlast = min(lo + 32 * q + 32, g.row_end - 1);
+                wait_prev(rlast);
+                const int r = lo + 32 * q + 1 + lane;
                 bchunk = r < g.row_end ? __ldcg(&bnd_prev[r]) : 0.f;
             }
-            __syncwarp();
-            const float Lsh = __shfl_up_sync(FULL, cur, 1);
-            const float bL = __shfl_sync(FULL, bchunk, (s - 1) & 31);
-            const int i = i0 - lane;
-            const bool active = valid && i > lo && i < g.row_end;
-            if (active) {
-                float nv;
-                if (strip == 0 && lane == 0) {
-                    nv = cur;
-                    const float *ra = &dring[((i - 1 + k) & 63) * 64 + 1];
-                    const float *rb = &dring[((i - 1) & 63) * 64 + 1];
-                    for (int q = 0; q < k; ++q) nv += ra[q] - rb[q];
-                } else {
-                    const float L = lane == 0 ? bL : Lsh;
-                    const float *r1 = &dring[((i + k - 1) & 63) * 64 + lane];
-                    const float *r0 = &dring[((i - 1) & 63) * 64 + lane];
-                    nv = L + cur;
-                    nv = nv - prevL;
-                    nv = nv + r1[k];
-                    nv = nv - r1[0];
-                    nv = nv - r0[k];
-                    nv = nv + r0[0];
-                    prevL = L;
+            const int send = min(32 * q + 32, nsteps);
+            for (int s = 32 * q + 1; s <= send; ++s) {
+                const float Lsh = __shfl_up_sync(FULL, cur, 1);
+                const float bL = __shfl_sync(FULL, bchunk, (s - 1) & 31);
+                const int i = lo + s - lane;
+                if (strip == 0) {
+                    // first column (core:3367-3372): differences by lanes q < k, additions in order by lane 0
+                    const int i0 = lo + s;
+                    if (i0 < g.row_end) {
+                        float sum = cur;      // only lane 0's value is used
+                        const float e = lane < k ? dval(i0 - 1 + k, 1 + lane) - dval(i0 - 1, 1 + lane) : 0.f;
+                        for (int t = 0; t < k; ++t) sum += __shfl_sync(FULL, e, t);
+                        if (lane == 0) { cur = sum; emit(i0, sum); }
+                    }
                 }
-                cur = nv;
-                tile[(i & 31) * 32 + lane] = nv;
-                if (has_next && lane == 31) __stcg(&bnd_next[i], nv);
+                if (valid && i > lo && i < g.row_end && !skip0) {
+                    const int o0 = (o1 - 64 * k) & 8191, p0 = (p1 - 64 * k) & 8191;
+                    float t1 = r2a[p1 + k] - r1a[o1 + k], t2 = r2a[p1] - r1a[o1];
+                    float t3 = r2a[p0 + k] - r1a[o0 + k], t4 = r2a[p0] - r1a[o0];
+                    t1 *= t1; t2 *= t2; t3 *= t3; t4 *= t4;
+                    if (SELF) {
+                        const bool rowz = i + k - 1 >= g.ylim;
+                        if (rowz || colz) t1 = 0.f;
+                        if (rowz) t2 = 0.f;
+                        if (colz) t3 = 0.f;
+                    }
+                    const float L = lane == 0 ? bL : Lsh;
+                    float nv = L + cur;
+                    nv = nv - prevL;
+                    nv = nv + t1;
+                    nv = nv - t2;
+                    nv = nv - t3;
+                    nv = nv + t4;
+                    prevL = L;
+                    cur = nv;
+                    emit(i, nv);
+                    if (has_next && lane == 31) __stcg(&bnd_next[i], nv);
+                }
+                o1 = (o1 + 64) & 8191;
+                p1 = (p1 + 64) & 8191;
             }
-            __syncwarp();
-            const int idone = i0 - 31;      // the row lane 31 has just finished
-            if (idone > lo && idone < g.row_end) emit_row(idone, tile[(idone & 31) * 32 + lane]);
+            if (has_next && lane == 31) {      // rows <= lo + send - 31 of the last column are final
+                __threadfence();
+                const int done = lo + send - 31;
+                if (done > lo) *prog_next = min(done, g.row_end - 1) + 1;
+            }
         }
-        __syncwarp();
-        float *t = bnd_prev; bnd_prev = bnd_next; bnd_next = t;
+        lf_cp_async_wait_all();
+        __syncthreads();
     }
 }
 
@@ -416,24 +508,27 @@ __global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Disparity matching (core:3576-3608): one thread per position of the dense grid. Only element [0] of the sorted
-// list and the shape flag are consumed downstream (core:294, 310, 503, 510).
+// Disparity matching (core:3576-3608): one thread per position, walking the skewed layout k_sat2 writes so that
+// the 169 plane reads are coalesced. Only element [0] of the sorted list and the shape flag are consumed
+// downstream (core:294, 310, 503, 510); the full std::sort is emulated only where the minimum is tied.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_stereo_argmin(const float *__restrict__ sums, int w, int h, int nDisp, int row_end, int col_end, float threshold,
-                                unsigned *__restrict__ out_first, unsigned char *__restrict__ out_shape, unsigned *tie_counter)
+__global__ void k_stereo_argmin(const float *__restrict__ sums, size_t plane_stride, int w, int nDisp, int lo, int row_end, int col_end,
+                                int nstrips, int SR, float threshold, unsigned *__restrict__ out_first, unsigned char *__restrict__ out_shape)
 {
     const int Ns = 2 * nDisp + 1, np = Ns * Ns;
-    const size_t plane = (size_t) w * h;
-    const int ww = col_end - nDisp, hh = row_end - nDisp;
-    const size_t total = (size_t) ww * hh;
+    const size_t total = (size_t) nstrips * SR * 32;
     for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
-        const int i = nDisp + (int) (t / ww), j = nDisp + (int) (t % ww);
+        const int lane = (int) (t & 31);
+        const size_t rs = t >> 5;
+        const int strip = (int) (rs / SR), sidx = (int) (rs - (size_t) strip * SR);
+        const int i = lo + sidx - lane, j = lo + (strip << 5) + lane;
+        if (i < lo || i >= row_end || j >= col_end) continue;
         const int k_r = i * w + j;
         float best = 0.f;
         int nmin = 0, amin = 0, c = 0;
         for (int djx = 0; djx < Ns; ++djx)
             for (int dix = 0; dix < Ns; ++dix, ++c) {
-                const float v = sums[(size_t) (djx + dix * Ns) * plane + k_r];
+                const float v = sums[(size_t) (djx + dix * Ns) * plane_stride + t];
                 if (c == 0 || v < best) { best = v; nmin = 1; amin = c; }
                 else if (v == best) nmin++;
             }
@@ -443,12 +538,11 @@ __global__ void k_stereo_argmin(const float *__restrict__ sums, int w, int h, in
             c = 0;
             for (int djx = 0; djx < Ns; ++djx)
                 for (int dix = 0; dix < Ns; ++dix, ++c) {
-                    td[c].d = sums[(size_t) (djx + dix * Ns) * plane + k_r];
+                    td[c].d = sums[(size_t) (djx + dix * Ns) * plane_stride + t];
                     td[c].i = (unsigned) (k_r + (dix - nDisp) * w + (djx - nDisp));
                 }
             lfs_sort(td, np);
             first = td[0].i;
-            if (tie_counter) atomicAdd(tie_counter, 1u);
         }
         out_first[k_r] = first;
         out_shape[k_r] = best < threshold ? 1 : 0;

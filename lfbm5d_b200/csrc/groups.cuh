@@ -14,6 +14,11 @@ struct GroupArgs {
     const unsigned char *shape;                   // [A][plane]
     const float *nsym, *bsym;                     // [A][C][plane]
     float *numsym, *densym;
+    // staging for the ordered aggregation kernel (k_aggregate): filtered patches, weights, positions, flags
+    float *zbuf;                                  // [R][N][A][C][k2]
+    float *wbuf;                                  // [R][C]
+    unsigned *spos;                               // [R][N][A] flat position of every gathered patch
+    unsigned char *gflag;                         // [R][A] 1 = this SAI's patches of the group are aggregated
     LfWindow win;
 };
 
@@ -405,7 +410,9 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     for (int t = tid; t < nSx * A; t += nth) {
         const int n = t / A, st = t - n * A;
         const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
-        spos[t] = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
+        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
+        spos[t] = pv;
+        g.spos[((size_t) r * g.N + n) * A + st] = pv;
     }
     if (tid == 0) {
         unsigned size = 0;
@@ -433,6 +440,8 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         }
     }
     __syncthreads();
+    if (tid < A)      // core:486, :503: which SAIs receive this group's patches
+        g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
     const bool use_sadct = sh.use_sadct != 0;
     const int npatch = nSx * A;
 
@@ -523,18 +532,119 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         }
         // ---- inverse 2-D transform (core:489-493) ----
         lf_t2d(Z, npatch, g, false);
-        // ---- aggregation (core:496-526) ----
+        // ---- stage the filtered patches and the weight; k_aggregate adds them in the reference's order ----
+        if (tid == 0) g.wbuf[(size_t) r * g.C + c] = wgt;
         for (int t = tid; t < npatch * k2; t += nth) {
             const int pa = t >> (2 * g.log2k), pq = t & (k2 - 1);
             const int p = pq >> g.log2k, q = pq & (k - 1);
-            const int st = pa % A;
-            if (g.win.proc[st]) continue;
-            if (g.tau_4D == 6 && st != g.pst && !sh.mask[st]) continue;
-            const size_t dst = ((size_t) st * g.C + c) * plane + spos[pa] + (size_t) p * w + q;
-            const float kw = c_tab.kaiser[pq] * wgt;
-            atomicAdd(g.numsym + dst, kw * Z[pa * PS + p * RS + q]);
-            atomicAdd(g.densym + dst, kw);
+            g.zbuf[(((size_t) r * g.N * A + pa) * g.C + c) * k2 + pq] = Z[pa * PS + p * RS + q];
         }
         __syncthreads();
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Weighted aggregation (core:496-526 / :1297-1327), deterministic and in the reference's order. One CTA per
+// 16x16 pixel tile of one SAI: every thread owns one pixel (all channels) and adds, in (reference patch, n) order —
+// the order the reference's serial loops produce for any given pixel — the contributions of every staged patch
+// that covers it: num += (kaiser*w)*z, den += kaiser*w. No atomics: results do not depend on scheduling, and
+// the accumulators are bit-identical to the reference's.
+// ------------------------------------------------------------------------------------------------------------
+struct AggArgs {
+    int C, A, k, N, log2N, w, h, nc;
+    const unsigned *bm_count;      // [R]
+    const unsigned *spos;          // [R][N][A]
+    const unsigned char *gflag;    // [R][A]
+    const float *zbuf, *wbuf;
+    float *numsym, *densym;
+    const int *arange, *brange;    // per tile row / tile column: first and last candidate reference row / column index
+    LfWindow win;
+};
+#define AGG_CAP 1024
+
+__global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
+{
+    __shared__ uint2 list[AGG_CAP];
+    __shared__ float skaiser[LF_MAXK * LF_MAXK];
+    __shared__ int wcount[8];
+    __shared__ int s_total;
+    const int st = blockIdx.z;
+    if (!g.win.mask[st] || g.win.proc[st]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = g.k, k2 = k * k, A = g.A, C = g.C, N = g.N;
+    const int y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+    const int y = y0 + (tid >> 4), x = x0 + (tid & 15);
+    const bool inimg = y < g.h && x < g.w;
+    const size_t plane = (size_t) g.w * g.h;
+    for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
+    const int a_lo = g.arange[2 * blockIdx.y], a_hi = g.arange[2 * blockIdx.y + 1];
+    const int b_lo = g.brange[2 * blockIdx.x], b_hi = g.brange[2 * blockIdx.x + 1];
+    const int nb = b_hi - b_lo + 1;
+    const int ncand = (a_hi >= a_lo && nb > 0) ? (a_hi - a_lo + 1) * nb * N : 0;
+    float num[3] = { 0.f, 0.f, 0.f }, den[3] = { 0.f, 0.f, 0.f };
+    const size_t pix = ((size_t) st * C) * plane + (size_t) y * g.w + x;
+    if (inimg)
+        for (int c = 0; c < C; ++c) { num[c] = g.numsym[pix + c * plane]; den[c] = g.densym[pix + c * plane]; }
+    if (tid == 0) s_total = 0;
+    __syncthreads();
+    const int yw0 = y0 + 2 * warp;      // this warp owns tile rows yw0, yw0 + 1
+
+    int base = 0;
+    while (base < ncand || s_total > 0) {
+        // ---- fill the list with the next covering patches, preserving (r, n) order ----
+        while (base < ncand && s_total + 256 <= AGG_CAP) {
+            const int qd = base + tid;
+            bool hit = false;
+            uint2 e = make_uint2(0u, 0u);
+            if (qd < ncand) {
+                const int n = qd & (N - 1), ab = qd >> g.log2N;
+                const int a = a_lo + ab / nb, b = b_lo + ab % nb;
+                const int r = a * g.nc + b;
+                if (n < (int) g.bm_count[r] && g.gflag[(size_t) r * A + st]) {
+                    const unsigned pos = g.spos[((size_t) r * N + n) * A + st];
+                    const int py = (int) (pos / (unsigned) g.w), px = (int) (pos % (unsigned) g.w);
+                    if (py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0) {
+                        hit = true;
+                        e = make_uint2(((unsigned) py << 16) | (unsigned) px, (unsigned) (r * N + n));
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) wcount[warp] = __popc(m);
+            __syncthreads();
+            int off = s_total;
+            for (int wv = 0; wv < warp; ++wv) off += wcount[wv];
+            if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = e;
+            __syncthreads();
+            if (tid == 0) { int t2 = s_total; for (int wv = 0; wv < 8; ++wv) t2 += wcount[wv]; s_total = t2; }
+            base += 256;
+            __syncthreads();
+        }
+        // ---- add the listed patches in order ----
+        const int cnt = s_total;
+        for (int i = 0; i < cnt; ++i) {
+            const uint2 e = list[i];
+            const int py = (int) (e.x >> 16), px = (int) (e.x & 0xffffu);
+            if (py > yw0 + 1 || py + k <= yw0) continue;          // warp-uniform: patch does not reach this warp's rows
+            const int dy = y - py, dx = x - px;
+            if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
+                const int pq = dy * k + dx;
+                const unsigned inst = e.y;
+                const int r = (int) (inst >> g.log2N);
+                const float kv = skaiser[pq];
+                const float *zp = g.zbuf + ((size_t) inst * A + st) * C * k2 + pq;
+                for (int c = 0; c < C; ++c) {
+                    const float kw = kv * g.wbuf[(size_t) r * C + c];
+                    num[c] += kw * zp[c * k2];
+                    den[c] += kw;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+    }
+    if (inimg)
+        for (int c = 0; c < C; ++c) { g.numsym[pix + c * plane] = num[c]; g.densym[pix + c * plane] = den[c]; }
 }

@@ -116,10 +116,11 @@ struct lfbm5d_ctx {
     int num_sms = 148;
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
-    DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, descs, bnd, rowmap, colmap, rows, cols, counters;
+    DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
+           zbuf, wbuf, spos, gflag, arange, brange;
     lfbm5d_stats stats{};
     bool timing = false;
-    cudaEvent_t ev[4]{};
+    cudaEvent_t ev[5]{};
     unsigned max_passes = 0;
     std::vector<unsigned> sched;
     bool geom_valid = false;
@@ -259,6 +260,24 @@ int upload_grid(lfbm5d_ctx *ctx, const PassCfg &pc)
     CK(cudaMemcpyAsync(ctx->colmap.p, colmap.data(), pc.wb * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->rows.p, pc.rows.data(), pc.rows.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->cols.p, pc.cols.data(), pc.cols.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // candidate reference rows / columns per 16-pixel tile row / column of the aggregation kernel: a patch gathered
+    // for a reference at row i_r starts within [i_r - n, i_r + n] (self +-nSim, then disparity +-nDisp)
+    auto ranges = [&](const std::vector<int> &idx, unsigned dim) {
+        const int ntile = (int) (dim + 15) / 16;
+        std::vector<int> rg(2 * ntile);
+        for (int t = 0; t < ntile; t++) {
+            const int lo_v = 16 * t - (int) pc.k - (int) pc.n + 1, hi_v = 16 * t + 15 + (int) pc.n;
+            int a_lo = (int) idx.size(), a_hi = -1;
+            for (int a = 0; a < (int) idx.size(); a++)
+                if (idx[a] >= lo_v && idx[a] <= hi_v) { a_lo = std::min(a_lo, a); a_hi = std::max(a_hi, a); }
+            rg[2 * t] = a_lo; rg[2 * t + 1] = a_hi;
+        }
+        return rg;
+    };
+    const std::vector<int> ar = ranges(pc.rows, pc.hb), br = ranges(pc.cols, pc.wb);
+    if (ctx->arange.ensure(ar.size() * 4) || ctx->brange.ensure(br.size() * 4)) return 1;
+    CK(cudaMemcpyAsync(ctx->arange.p, ar.data(), ar.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->brange.p, br.data(), br.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -271,12 +290,19 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
         ctx->densym.ensure(pc.A * pc.C * plane * 4) || ctx->est0.ensure(pc.A * plane * 4)) return 1;
     if (pc.step == 2 && ctx->bsym.ensure(pc.A * pc.C * plane * 4)) return 1;
     if (pc.N > 1 && (ctx->s_at.ensure(nself * R * 4) || ctx->s_mir.ensure(nself * R * 4))) return 1;
-    if (pc.A > 1 && ctx->sums.ensure((pc.A - 1) * Nd * Nd * plane * 4)) return 1;
+    // stereo sums in the skewed layout of k_sat2: [plane][strip][SR][32]
+    const size_t st_cols = pc.wb - 2 * pc.nDisp - pc.k + 1, st_rows = pc.hb - 2 * pc.nDisp - pc.k + 1;
+    const size_t st_strips = (st_cols + 31) / 32, st_SR = st_rows + 31;
+    if (pc.A > 1 && ctx->sums.ensure((pc.A - 1) * Nd * Nd * st_strips * st_SR * 32 * 4)) return 1;
     if (ctx->first.ensure(pc.A * plane * 4) || ctx->shape.ensure(pc.A * plane)) return 1;
     if (ctx->bmcount.ensure(R * 4) || ctx->bmidx.ensure(R * (pc.N + 1) * 4)) return 1;
     const size_t nplanes = nself + (pc.A - 1) * Nd * Nd;
-    if (ctx->descs.ensure(nplanes * sizeof(SatDesc)) || ctx->bnd.ensure(nplanes * 2 * pc.hb * 4)) return 1;
+    const size_t max_strips = std::max(st_strips, (size_t) (pc.wb - 2 * pc.n + 31) / 32);
+    if (ctx->satplanes.ensure(nplanes * sizeof(SatPlane)) || ctx->satgroups.ensure(nplanes * sizeof(SatGroup)) ||
+        ctx->bnd.ensure(nplanes * max_strips * pc.hb * 4) || ctx->progress.ensure((nplanes * max_strips + 4) * 4)) return 1;
     if (ctx->counters.ensure(64 * 8)) return 1;
+    if (ctx->zbuf.ensure(R * pc.N * pc.A * pc.C * pc.k * pc.k * 4) || ctx->wbuf.ensure(R * pc.C * 4) ||
+        ctx->spos.ensure(R * pc.N * pc.A * 4) || ctx->gflag.ensure(R * pc.A)) return 1;
     return 0;
 }
 
@@ -299,52 +325,87 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     const float *est0 = ctx->est0.as<float>();
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
 
-    // ---- plane descriptors: self similarity first, then every other SAI of the window ----
-    std::vector<SatDesc> descs;
+    // ---- offset planes: groups of <= 13 planes sharing their source rows (same images, same row offset) ----
+    std::vector<SatPlane> planes;
+    std::vector<SatGroup> groups;
     std::vector<int> stereo_sai;
-    for (int ddk = 0; ddk < nself; ddk++) {
-        const int di = ddk / Ns, djx = ddk % Ns;
-        SatDesc d{};
-        d.img1 = est0 + (size_t) pst * plane; d.img2 = d.img1;
-        d.dk = di * (int) pc.wb + djx - (int) pc.nSim;                 // core:3331
-        d.out_at = ctx->s_at.as<float>() + (size_t) ddk * R;
-        d.out_mir = ctx->s_mir.as<float>() + (size_t) ddk * R;
-        d.mir_di = di; d.mir_dc = (int) pc.nSim - djx;
-        d.bnd = ctx->bnd.as<float>() + (size_t) descs.size() * 2 * pc.hb;
-        descs.push_back(d);
-    }
+    const float *ref0 = est0 + (size_t) pst * plane;
+    for (int di = 0; di < (nself ? (int) pc.nSim + 1 : 0); di++)
+        for (int djx0 = 0; djx0 < Ns; djx0 += SAT_NW) {
+            SatGroup G{};
+            G.img1 = ref0; G.img2 = ref0; G.oy = di; G.oxmin = djx0 - (int) pc.nSim;      // core:3331: dk = di*w + djx - nSim
+            G.first_plane = (int) planes.size();
+            for (int djx = djx0; djx < std::min(Ns, djx0 + SAT_NW); djx++) {
+                SatPlane P{};
+                const int ddk = di * Ns + djx;
+                P.ox = djx - (int) pc.nSim;
+                P.out_at = ctx->s_at.as<float>() + (size_t) ddk * R;
+                P.out_mir = ctx->s_mir.as<float>() + (size_t) ddk * R;
+                P.mir_di = di; P.mir_dc = (int) pc.nSim - djx;
+                planes.push_back(P);
+                G.nplanes++;
+            }
+            groups.push_back(G);
+        }
+    const int nself_groups = (int) groups.size(), nself_planes = (int) planes.size();
+    const int st_lo = pc.nDisp, st_row_end = pc.hb - pc.nDisp - pc.k + 1, st_col_end = pc.wb - pc.nDisp - pc.k + 1;
+    const int st_strips = (st_col_end - st_lo + 31) / 32, st_SR = (st_row_end - st_lo) + 31;
+    const size_t st_stride = (size_t) st_strips * st_SR * 32;
     int slot = 0;
     for (int st = 0; st < (int) pc.A; st++) {
         if (st == pst || !win.mask[st]) continue;
-        for (int ddk = 0; ddk < nd2; ddk++) {
-            const int di = ddk / Nd, dj = ddk % Nd;
-            SatDesc d{};
-            d.img1 = est0 + (size_t) pst * plane; d.img2 = est0 + (size_t) st * plane;
-            d.dk = di * (int) pc.wb + dj - (int) (pc.nDisp * (1 + pc.wb));   // core:3516
-            d.out_plane = ctx->sums.as<float>() + ((size_t) slot * nd2 + ddk) * plane;
-            d.bnd = ctx->bnd.as<float>() + (size_t) descs.size() * 2 * pc.hb;
-            descs.push_back(d);
+        for (int di = 0; di < Nd; di++) {      // core:3516: dk = (di - nDisp)*w + (dj - nDisp)
+            SatGroup G{};
+            G.img1 = ref0; G.img2 = est0 + (size_t) st * plane; G.oy = di - (int) pc.nDisp; G.oxmin = -(int) pc.nDisp;
+            G.first_plane = (int) planes.size();
+            for (int dj = 0; dj < Nd; dj++) {
+                SatPlane P{};
+                P.ox = dj - (int) pc.nDisp;
+                P.out_skew = ctx->sums.as<float>() + ((size_t) slot * nd2 + (size_t) di * Nd + dj) * st_stride;
+                planes.push_back(P);
+                G.nplanes++;
+            }
+            groups.push_back(G);
         }
         stereo_sai.push_back(st);
         slot++;
     }
-    if (!descs.empty())
-        CK(cudaMemcpyAsync(ctx->descs.p, descs.data(), descs.size() * sizeof(SatDesc), cudaMemcpyHostToDevice, ctx->stream));
+    if (!planes.empty()) {
+        CK(cudaMemcpyAsync(ctx->satplanes.p, planes.data(), planes.size() * sizeof(SatPlane), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->satgroups.p, groups.data(), groups.size() * sizeof(SatGroup), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int self_strips = ((int) pc.wb - 2 * (int) pc.n + 31) / 32;
+    int *ticket = ctx->progress.as<int>();      // [0]: self launch, [1]: stereo launch; flags follow
+    int *flags = ticket + 4;
+    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) std::max(self_strips, st_strips)) * 4, ctx->stream));
     cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
     if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
     if (nself > 0) {
         LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
         SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n; g.dlo = pc.n;
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n;
+        g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.SR = 0;
         g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
-        LAUNCH(ctx, k_sat_planes<true>, nself, 32, 0, g, ctx->descs.as<SatDesc>());
+        const size_t smem = 2 * 128 * 64 * 4 + (size_t) (pc.hb + pc.wb) * 4;
+        auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
+        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        kfn<<<nself_groups * self_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>(), ctx->satplanes.as<SatPlane>(),
+                                                                            nself_groups, ctx->bnd.as<float>(), flags, ticket);
+        ctx->stats.kernel_launches++;
     }
     if (slot > 0) {
         SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.nDisp; g.row_end = pc.hb - pc.nDisp - pc.k + 1;
-        g.col_end = pc.wb - pc.nDisp - pc.k + 1; g.dlo = pc.nDisp;
-        LAUNCH(ctx, k_sat_planes<false>, slot * nd2, 32, 0, g, ctx->descs.as<SatDesc>() + nself);
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
+        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
+        const size_t smem = 2 * 128 * 64 * 4;
+        const int ngroups = (int) groups.size() - nself_groups;
+        auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
+        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        kfn<<<ngroups * st_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>() + nself_groups,
+                                                                     ctx->satplanes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
+        ctx->stats.kernel_launches++;
     }
+    (void) nself_planes;
     if (ctx->timing) CK(cudaEventRecord(sat1, ctx->stream));
     // ---- selection ----
     if (nself > 0) {
@@ -359,11 +420,9 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     }
     for (int s = 0; s < slot; s++) {
         const int st = stereo_sai[s];
-        const int row_end = pc.hb - pc.nDisp - pc.k + 1, col_end = pc.wb - pc.nDisp - pc.k + 1;
-        const size_t total = (size_t) (row_end - pc.nDisp) * (col_end - pc.nDisp);
-        LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, total, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * plane, (int) pc.wb,
-               (int) pc.hb, (int) pc.nDisp, row_end, col_end, threshold, ctx->first.as<unsigned>() + (size_t) st * plane,
-               ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned *) nullptr);
+        LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
+               (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
+               ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane);
     }
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
 
@@ -379,6 +438,8 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     ga.first = ctx->first.as<unsigned>(); ga.shape = ctx->shape.as<unsigned char>();
     ga.nsym = ctx->nsym.as<float>(); ga.bsym = ctx->bsym.as<float>();
     ga.numsym = ctx->numsym.as<float>(); ga.densym = ctx->densym.as<float>();
+    ga.zbuf = ctx->zbuf.as<float>(); ga.wbuf = ctx->wbuf.as<float>(); ga.spos = ctx->spos.as<unsigned>();
+    ga.gflag = ctx->gflag.as<unsigned char>();
     ga.win = win;
     const size_t smem = (size_t) pc.N * pc.A * ga.PS * 4 * (pc.step == 2 ? 2 : 1);
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
@@ -386,6 +447,20 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     kfn<<<R, 256, smem, ctx->stream>>>(ga);
     ctx->stats.kernel_launches++;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    {   // ordered aggregation of the staged patches
+        AggArgs aa{};
+        aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
+        while ((1u << aa.log2N) < pc.N) aa.log2N++;
+        aa.w = pc.wb; aa.h = pc.hb; aa.nc = nc;
+        aa.bm_count = ctx->bmcount.as<unsigned>(); aa.spos = ctx->spos.as<unsigned>(); aa.gflag = ctx->gflag.as<unsigned char>();
+        aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
+        aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
+        aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
+        aa.win = win;
+        dim3 grid((pc.wb + 15) / 16, (pc.hb + 15) / 16, pc.A);
+        LAUNCH(ctx, k_aggregate, grid, 256, 0, aa);
+    }
     CK(cudaGetLastError());
     ctx->stats.window_passes++;
     if (ctx->timing) {
@@ -393,11 +468,12 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         CK(cudaEventCreate(&e2));
         CK(cudaEventRecord(e2, ctx->stream));
         CK(cudaEventSynchronize(e2));
-        float a = 0, b = 0, c = 0;
+        float a = 0, b = 0, c = 0, d = 0;
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&b, ctx->ev[1], e2);
+        cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[4]);
         cudaEventElapsedTime(&c, sat0, sat1);
-        ctx->stats.ms_block_matching += a; ctx->stats.ms_groups += b; ctx->stats.ms_sat += c;
+        cudaEventElapsedTime(&d, ctx->ev[4], e2);
+        ctx->stats.ms_block_matching += a; ctx->stats.ms_groups += b; ctx->stats.ms_sat += c; ctx->stats.ms_aggregate += d;
         cudaEventDestroy(e2);
     }
     return 0;
@@ -598,7 +674,8 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
-                      &ctx->bmidx, &ctx->descs, &ctx->bnd, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters };
+                      &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
