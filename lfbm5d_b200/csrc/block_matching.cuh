@@ -47,6 +47,13 @@ __device__ __forceinline__ void lf_cp_async_wait_all()
     asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
 }
 
+template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
 // Summed-area planes, v2. Work unit = (group of <= 13 planes sharing their source rows, 32-column strip): one warp
 // per plane; lane l owns column c0+l and runs one row behind lane l-1 (skewed wavefront, one shuffle per step).
 // The strips of a plane are pipelined across CTAs: strip c consumes the last column of strip c-1 through global
@@ -59,8 +66,10 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
                                                           int ngroups, float *bnd, int *progress, int *ticket_counter)
 {
     extern __shared__ float s_dyn[];
-    float *R1 = s_dyn, *R2 = s_dyn + 128 * 64;          // source-row rings of img1 / img2
-    int *s_maps = reinterpret_cast<int *>(s_dyn + 2 * 128 * 64);   // SELF: rowmap[h] then colmap[w]
+    // source-row rings of img1 / img2: 128 rows + K mirror rows (slot s < K is also stored at s + 128, so that the
+    // row K below any slot is always at slot + K without wrapping)
+    float *R1 = s_dyn, *R2 = s_dyn + (128 + K) * 64;
+    int *s_maps = reinterpret_cast<int *>(s_dyn + 2 * (128 + K) * 64);   // SELF: rowmap[h] then colmap[w]
     __shared__ int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -98,13 +107,19 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
         for (int t = tid; t < n; t += blockDim.x) {
             const int y = y0 + (t >> 7), c = t & 63, which = (t >> 6) & 1;
             if (which == 0) {
-                const int x = xb1 + c;
-                float *dst = &R1[(y & 127) * 64 + c];
-                if (x < w) lf_cp_async4(dst, G.img1 + (size_t) y * w + x); else *dst = 0.f;
+                const int x = xb1 + c, sl = y & 127;
+                float *dst = &R1[sl * 64 + c];
+                if (x < w) {
+                    lf_cp_async4(dst, G.img1 + (size_t) y * w + x);
+                    if (sl < K) lf_cp_async4(dst + 128 * 64, G.img1 + (size_t) y * w + x);
+                } else { *dst = 0.f; if (sl < K) dst[128 * 64] = 0.f; }
             } else {
-                const int yy = y + G.oy, x = xb2 + c;
-                float *dst = &R2[(yy & 127) * 64 + c];
-                if (yy >= 0 && yy < h && x >= 0 && x < w) lf_cp_async4(dst, G.img2 + (size_t) yy * w + x); else *dst = 0.f;
+                const int yy = y + G.oy, x = xb2 + c, sl = yy & 127;
+                float *dst = &R2[sl * 64 + c];
+                if (yy >= 0 && yy < h && x >= 0 && x < w) {
+                    lf_cp_async4(dst, G.img2 + (size_t) yy * w + x);
+                    if (sl < K) lf_cp_async4(dst + 128 * 64, G.img2 + (size_t) yy * w + x);
+                } else { *dst = 0.f; if (sl < K) dst[128 * 64] = 0.f; }
             }
         }
     };
@@ -187,32 +202,68 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
     }
 
     // ---- wavefront over the remaining rows in chunks of 32 steps (core:3365-3387 / :3550-3572) ----
-    // Ring offsets of this lane (floats): row i+k-1 -> o1 (img1) / p1 (img2), row i-1 -> (o1 - 64k) & 8191; both advance
-    // by one ring row per step.
+    // Per lane, ro1 / ro2 = byte offset of the ring row holding source row i-1 (img1) / i-1+oy (img2); source row
+    // i+K-1 is K ring rows further (mirror rows: no wrap). Both advance by one ring row (256 B) per step.
     const int nsteps = (Hh - 1) + 31;
     const int nchunks = (nsteps + 31) >> 5;
-    int o1 = ((lo + 1 - lane + k - 1) & 127) * 64;
-    int p1 = ((lo + 1 - lane + k - 1 + G.oy) & 127) * 64;
-    const float *r1a = R1 + lane, *r2a = R2 + lane + oxo;
+    const unsigned sb1 = (unsigned) __cvta_generic_to_shared(R1) + 4u * (unsigned) lane;
+    const unsigned sb2 = (unsigned) __cvta_generic_to_shared(R2) + 4u * (unsigned) (lane + oxo);
+    unsigned ro1 = (unsigned) (((lo + 1 - lane - 1) & 127) * 256);
+    unsigned ro2 = (unsigned) (((lo + 1 - lane - 1 + G.oy) & 127) * 256);
     const bool colz = SELF && (j + k - 1 >= g.xlim);
     const bool skip0 = strip == 0 && lane == 0;
+    // lane is active at steps s in [lane + 1, lane + Hh - 1]
+    const unsigned s_first = (valid && !skip0) ? (unsigned) (lane + 1) : 0x40000000u;
+    const unsigned s_span = (unsigned) (Hh - 1);
+    float *bptr = bnd_next + (lo - lane);          // bptr[s] = bnd_next[i]
+    auto step_general = [&](int s, float Lsh, float bL) {
+        if ((unsigned) s - s_first < s_span) {
+            const unsigned a1 = sb1 + ro1, a2 = sb2 + ro2;
+            float t1 = lf_lds<K * 256 + K * 4>(a2) - lf_lds<K * 256 + K * 4>(a1);
+            float t2 = lf_lds<K * 256>(a2) - lf_lds<K * 256>(a1);
+            float t3 = lf_lds<K * 4>(a2) - lf_lds<K * 4>(a1);
+            float t4 = lf_lds<0>(a2) - lf_lds<0>(a1);
+            t1 *= t1; t2 *= t2; t3 *= t3; t4 *= t4;
+            const int i = lo + s - lane;
+            if (SELF) {
+                const bool rowz = i + k - 1 >= g.ylim;
+                if (rowz || colz) t1 = 0.f;
+                if (rowz) t2 = 0.f;
+                if (colz) t3 = 0.f;
+            }
+            const float L = lane == 0 ? bL : Lsh;
+            float nv = L + cur;
+            nv = nv - prevL;
+            nv = nv + t1;
+            nv = nv - t2;
+            nv = nv - t3;
+            nv = nv + t4;
+            prevL = L;
+            cur = nv;
+            emit(i, nv);
+            if (has_next && lane == 31) __stcg(&bptr[s], nv);
+        }
+        ro1 = (ro1 + 256u) & 32767u;
+        ro2 = (ro2 + 256u) & 32767u;
+    };
     for (int q = 0; q < nchunks; ++q) {
         // stage the source rows of the next chunk while this one runs
         load_rows(lo + 32 * (q + 1) + k, lo + 32 * (q + 1) + 32 + k - 1);
         if (hasplane) {
-            float bchunk = 0.f;
+            const int send = min(32 * q + 32, nsteps);
             if (strip > 0) {
                 const int rlast = min(lo + 32 * q + 32, g.row_end - 1);
                 wait_prev(rlast);
                 const int r = lo + 32 * q + 1 + lane;
-                bchunk = r < g.row_end ? __ldcg(&bnd_prev[r]) : 0.f;
-            }
-            const int send = min(32 * q + 32, nsteps);
-            for (int s = 32 * q + 1; s <= send; ++s) {
-                const float Lsh = __shfl_up_sync(FULL, cur, 1);
-                const float bL = __shfl_sync(FULL, bchunk, (s - 1) & 31);
-                const int i = lo + s - lane;
-                if (strip == 0) {
+                const float bchunk = r < g.row_end ? __ldcg(&bnd_prev[r]) : 0.f;
+                for (int s = 32 * q + 1; s <= send; ++s) {
+                    const float Lsh = __shfl_up_sync(FULL, cur, 1);
+                    const float bL = __shfl_sync(FULL, bchunk, (s - 1) & 31);
+                    step_general(s, Lsh, bL);
+                }
+            } else {
+                for (int s = 32 * q + 1; s <= send; ++s) {
+                    const float Lsh = __shfl_up_sync(FULL, cur, 1);
                     // first column (core:3367-3372): differences by lanes q < k, additions in order by lane 0
                     const int i0 = lo + s;
                     if (i0 < g.row_end) {
@@ -221,32 +272,8 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
                         for (int t = 0; t < k; ++t) sum += __shfl_sync(FULL, e, t);
                         if (lane == 0) { cur = sum; emit(i0, sum); }
                     }
+                    step_general(s, Lsh, 0.f);
                 }
-                if (valid && i > lo && i < g.row_end && !skip0) {
-                    const int o0 = (o1 - 64 * k) & 8191, p0 = (p1 - 64 * k) & 8191;
-                    float t1 = r2a[p1 + k] - r1a[o1 + k], t2 = r2a[p1] - r1a[o1];
-                    float t3 = r2a[p0 + k] - r1a[o0 + k], t4 = r2a[p0] - r1a[o0];
-                    t1 *= t1; t2 *= t2; t3 *= t3; t4 *= t4;
-                    if (SELF) {
-                        const bool rowz = i + k - 1 >= g.ylim;
-                        if (rowz || colz) t1 = 0.f;
-                        if (rowz) t2 = 0.f;
-                        if (colz) t3 = 0.f;
-                    }
-                    const float L = lane == 0 ? bL : Lsh;
-                    float nv = L + cur;
-                    nv = nv - prevL;
-                    nv = nv + t1;
-                    nv = nv - t2;
-                    nv = nv - t3;
-                    nv = nv + t4;
-                    prevL = L;
-                    cur = nv;
-                    emit(i, nv);
-                    if (has_next && lane == 31) __stcg(&bnd_next[i], nv);
-                }
-                o1 = (o1 + 64) & 8191;
-                p1 = (p1 + 64) & 8191;
             }
             if (has_next && lane == 31) {      // rows <= lo + send - 31 of the last column are final
                 __threadfence();

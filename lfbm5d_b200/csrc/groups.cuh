@@ -394,24 +394,32 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     extern __shared__ float smem[];
     __shared__ GroupShape sh;
     __shared__ float red[8];
-    __shared__ unsigned spos[LF_MAXN * LF_MAXA];
+    __shared__ unsigned sofs[LF_MAXN * LF_MAXA];          // per gathered patch: st*C*plane + position
+    __shared__ unsigned char szero[LF_MAXN * LF_MAXA];    // patch reads as zeros (empty SAI, or column w-k: core:1697)
     constexpr int A = ASW * ASW;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x;
     const int r = blockIdx.x;
     const int k = g.k, k2 = k * k, w = g.w;
-    const size_t plane = (size_t) g.w * g.h;
+    const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
     const int nSx = (int) g.bm_count[r];
     const int lg = 31 - __clz(nSx);
     const int PS = g.PS, RS = g.RS;
     float *X = smem;
     float *E = smem + (size_t) g.N * A * PS;      // step 2 only (N >= nSx except the duplicated single match: N >= 2)
+    // thread <-> (sub, pq): a thread keeps its pixel/coefficient position and strides over patches
+    const int PPI = 256 >> (2 * g.log2k);          // patches handled per sweep of the block (1 for k = 16, 4 for k = 8)
+    const int sub = tid >> (2 * g.log2k), pq = tid & (k2 - 1);
+    const int p = pq >> g.log2k, q = pq & (k - 1);
+    const int poff = p * RS + q;
+    const int npatch = nSx * A;
 
-    for (int t = tid; t < nSx * A; t += nth) {
+    for (int t = tid; t < npatch; t += 256) {
         const int n = t / A, st = t - n * A;
         const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
         const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
-        spos[t] = pv;
+        sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv;
+        szero[t] = (!g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k) ? 1 : 0;
         g.spos[((size_t) r * g.N + n) * A + st] = pv;
     }
     if (tid == 0) {
@@ -443,23 +451,22 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     if (tid < A)      // core:486, :503: which SAIs receive this group's patches
         g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
     const bool use_sadct = sh.use_sadct != 0;
-    const int npatch = nSx * A;
+    float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
 
     for (int c = 0; c < g.C; ++c) {
-        // ---- gather (core:286-299): raw patches; a patch whose column is w-k reads as zeros (core:1697) ----
-        for (int t = tid; t < npatch * k2; t += nth) {
-            const int pa = t >> (2 * g.log2k), pq = t & (k2 - 1);
-            const int p = pq >> g.log2k, q = pq & (k - 1);
-            const int st = pa % A;
-            const unsigned pos = spos[pa];
-            float xv = 0.f, ev = 0.f;
-            if (g.win.mask[st] && (int) (pos % (unsigned) w) < w - k) {
-                const size_t src = ((size_t) st * g.C + c) * plane + pos + (size_t) p * w + q;
-                xv = g.nsym[src];
-                if (STEP == 2) ev = g.bsym[src];
+        // ---- gather (core:286-299): raw patches ----
+        {
+            const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
+            for (int pa = sub; pa < npatch; pa += PPI) {
+                float xv = 0.f, ev = 0.f;
+                if (!szero[pa]) {
+                    const unsigned src = sofs[pa] + tofs;
+                    xv = g.nsym[src];
+                    if (STEP == 2) ev = g.bsym[src];
+                }
+                X[pa * PS + poff] = xv;
+                if (STEP == 2) E[pa * PS + poff] = ev;
             }
-            X[pa * PS + p * RS + q] = xv;
-            if (STEP == 2) E[pa * PS + p * RS + q] = ev;
         }
         __syncthreads();
         // ---- 2-D spatial transform; patches that read as zeros stay zero under any of the transforms ----
@@ -467,9 +474,8 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         if (STEP == 2) lf_t2d(E, npatch, g, true);
         // ---- angular transform (core:354-360) ----
         if (g.tau_4D != 4) {
-            for (int t = tid; t < nSx * k2; t += nth) {
-                const int n = t >> (2 * g.log2k), pq = t & (k2 - 1);
-                const int off = n * A * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+            for (int n = sub; n < nSx; n += PPI) {
+                const int off = n * A * PS + poff;
                 for (int rep = 0; rep < STEP; ++rep) {
                     float *B = rep == 0 ? X : E;
                     float v[A];
@@ -491,9 +497,8 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         }
         // ---- 5th dimension + shrinkage (core:371-410 / :1170-1210) ----
         float wpart = 0.f;
-        for (int t = tid; t < A * k2; t += nth) {
-            const int st = t >> (2 * g.log2k), pq = t & (k2 - 1);
-            const int base = st * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+        for (int st = sub; st < A; st += PPI) {
+            const int base = st * PS + poff;
             const bool shrink = !use_sadct || sh.mask_dct[st];
             const int ns = A * PS;
             switch (nSx) {
@@ -511,9 +516,8 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         float *Z = STEP == 1 ? X : E;
         // ---- inverse angular transform (core:432-451) ----
         if (g.tau_4D != 4) {
-            for (int t = tid; t < nSx * k2; t += nth) {
-                const int n = t >> (2 * g.log2k), pq = t & (k2 - 1);
-                const int off = n * A * PS + (pq >> g.log2k) * RS + (pq & (k - 1));
+            for (int n = sub; n < nSx; n += PPI) {
+                const int off = n * A * PS + poff;
                 float v[A];
 #pragma unroll
                 for (int st = 0; st < A; ++st) v[st] = Z[off + st * PS];
@@ -534,15 +538,10 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         lf_t2d(Z, npatch, g, false);
         // ---- stage the filtered patches and the weight; k_aggregate adds them in the reference's order ----
         if (tid == 0) g.wbuf[(size_t) r * g.C + c] = wgt;
-        for (int t = tid; t < npatch * k2; t += nth) {
-            const int pa = t >> (2 * g.log2k), pq = t & (k2 - 1);
-            const int p = pq >> g.log2k, q = pq & (k - 1);
-            g.zbuf[(((size_t) r * g.N * A + pa) * g.C + c) * k2 + pq] = Z[pa * PS + p * RS + q];
-        }
+        for (int pa = sub; pa < npatch; pa += PPI) zdst[(pa * g.C + c) * k2] = Z[pa * PS + poff];
         __syncthreads();
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------
 // Weighted aggregation (core:496-526 / :1297-1327), deterministic and in the reference's order. One CTA per
@@ -561,11 +560,12 @@ struct AggArgs {
     const int *arange, *brange;    // per tile row / tile column: first and last candidate reference row / column index
     LfWindow win;
 };
-#define AGG_CAP 1024
+#define AGG_CAP 768
+struct AggEntry { unsigned yx, zidx; float w[3]; };
 
 __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
 {
-    __shared__ uint2 list[AGG_CAP];
+    __shared__ AggEntry list[AGG_CAP];
     __shared__ float skaiser[LF_MAXK * LF_MAXK];
     __shared__ int wcount[8];
     __shared__ int s_total;
@@ -580,8 +580,7 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
     for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
     const int a_lo = g.arange[2 * blockIdx.y], a_hi = g.arange[2 * blockIdx.y + 1];
     const int b_lo = g.brange[2 * blockIdx.x], b_hi = g.brange[2 * blockIdx.x + 1];
-    const int nb = b_hi - b_lo + 1;
-    const int ncand = (a_hi >= a_lo && nb > 0) ? (a_hi - a_lo + 1) * nb * N : 0;
+    const int nbn = (b_hi - b_lo + 1) * N;                 // candidates per reference row: (column, n)
     float num[3] = { 0.f, 0.f, 0.f }, den[3] = { 0.f, 0.f, 0.f };
     const size_t pix = ((size_t) st * C) * plane + (size_t) y * g.w + x;
     if (inimg)
@@ -590,60 +589,70 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
     __syncthreads();
     const int yw0 = y0 + 2 * warp;      // this warp owns tile rows yw0, yw0 + 1
 
-    int base = 0;
-    while (base < ncand || s_total > 0) {
-        // ---- fill the list with the next covering patches, preserving (r, n) order ----
-        while (base < ncand && s_total + 256 <= AGG_CAP) {
-            const int qd = base + tid;
-            bool hit = false;
-            uint2 e = make_uint2(0u, 0u);
-            if (qd < ncand) {
-                const int n = qd & (N - 1), ab = qd >> g.log2N;
-                const int a = a_lo + ab / nb, b = b_lo + ab % nb;
-                const int r = a * g.nc + b;
-                if (n < (int) g.bm_count[r] && g.gflag[(size_t) r * A + st]) {
-                    const unsigned pos = g.spos[((size_t) r * N + n) * A + st];
-                    const int py = (int) (pos / (unsigned) g.w), px = (int) (pos % (unsigned) g.w);
-                    if (py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0) {
-                        hit = true;
-                        e = make_uint2(((unsigned) py << 16) | (unsigned) px, (unsigned) (r * N + n));
-                    }
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) wcount[warp] = __popc(m);
-            __syncthreads();
-            int off = s_total;
-            for (int wv = 0; wv < warp; ++wv) off += wcount[wv];
-            if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = e;
-            __syncthreads();
-            if (tid == 0) { int t2 = s_total; for (int wv = 0; wv < 8; ++wv) t2 += wcount[wv]; s_total = t2; }
-            base += 256;
-            __syncthreads();
-        }
-        // ---- add the listed patches in order ----
+    // add the listed patches in list order
+    auto flush = [&]() {
         const int cnt = s_total;
         for (int i = 0; i < cnt; ++i) {
-            const uint2 e = list[i];
-            const int py = (int) (e.x >> 16), px = (int) (e.x & 0xffffu);
+            const unsigned yx = list[i].yx;
+            const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);
             if (py > yw0 + 1 || py + k <= yw0) continue;          // warp-uniform: patch does not reach this warp's rows
             const int dy = y - py, dx = x - px;
             if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
                 const int pq = dy * k + dx;
-                const unsigned inst = e.y;
-                const int r = (int) (inst >> g.log2N);
                 const float kv = skaiser[pq];
-                const float *zp = g.zbuf + ((size_t) inst * A + st) * C * k2 + pq;
-                for (int c = 0; c < C; ++c) {
-                    const float kw = kv * g.wbuf[(size_t) r * C + c];
-                    num[c] += kw * zp[c * k2];
-                    den[c] += kw;
-                }
+                const float *zp = g.zbuf + (size_t) list[i].zidx * k2 + pq;
+                float z[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) z[c] = c < C ? zp[c * k2] : 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    if (c < C) {
+                        const float kw = kv * list[i].w[c];
+                        num[c] += kw * z[c];
+                        den[c] += kw;
+                    }
             }
         }
         __syncthreads();
         if (tid == 0) s_total = 0;
         __syncthreads();
+    };
+
+    if (a_hi >= a_lo && nbn > 0) {
+        for (int a = a_lo; a <= a_hi; ++a) {
+            for (int base = 0; base < nbn; base += 256) {
+                if (s_total + 256 > AGG_CAP) flush();
+                // ---- candidates (a, b, n) in the reference's order; keep those whose patch covers the tile ----
+                const int bn = base + tid;
+                bool hit = false;
+                AggEntry e;
+                e.yx = 0; e.zidx = 0; e.w[0] = e.w[1] = e.w[2] = 0.f;
+                if (bn < nbn) {
+                    const int n = bn & (N - 1), b = b_lo + (bn >> g.log2N);
+                    const int r = a * g.nc + b;
+                    if (n < (int) g.bm_count[r] && g.gflag[(size_t) r * A + st]) {
+                        const unsigned pos = g.spos[((size_t) r * N + n) * A + st];
+                        const int py = (int) (pos / (unsigned) g.w), px = (int) (pos - (unsigned) py * (unsigned) g.w);
+                        if (py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0) {
+                            hit = true;
+                            e.yx = ((unsigned) py << 16) | (unsigned) px;
+                            e.zidx = (unsigned) ((((size_t) r * N + n) * A + st) * C);
+                            for (int c = 0; c < C; ++c) e.w[c] = g.wbuf[(size_t) r * C + c];
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) wcount[warp] = __popc(m);
+                __syncthreads();
+                int off = s_total, tot = 0;
+                for (int wv = 0; wv < 8; ++wv) { if (wv < warp) off += wcount[wv]; tot += wcount[wv]; }
+                if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = e;
+                __syncthreads();
+                if (tid == 0) s_total += tot;
+                __syncthreads();
+            }
+        }
+        flush();
     }
     if (inimg)
         for (int c = 0; c < C; ++c) { g.numsym[pix + c * plane] = num[c]; g.densym[pix + c * plane] = den[c]; }

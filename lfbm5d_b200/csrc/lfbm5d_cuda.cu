@@ -386,7 +386,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n;
         g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.SR = 0;
         g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
-        const size_t smem = 2 * 128 * 64 * 4 + (size_t) (pc.hb + pc.wb) * 4;
+        const size_t smem = 2 * (128 + pc.k) * 64 * 4 + (size_t) (pc.hb + pc.wb) * 4;
         auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
         CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         kfn<<<nself_groups * self_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>(), ctx->satplanes.as<SatPlane>(),
@@ -397,7 +397,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         SatGeom g{};
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
         g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
-        const size_t smem = 2 * 128 * 64 * 4;
+        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
         const int ngroups = (int) groups.size() - nself_groups;
         auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
         CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
