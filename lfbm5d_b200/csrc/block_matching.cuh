@@ -37,16 +37,6 @@ struct SatGroup {
     int oy, oxmin, nplanes, first_plane;
 };
 
-__device__ __forceinline__ void lf_cp_async4(float *smem_dst, const float *gsrc)
-{
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void lf_cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
-}
-
 template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 {
     float v;
@@ -156,8 +146,7 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
     };
     auto wait_prev = [&](int need) {      // producer strip has published rows <= need (flag holds row + 1)
         if (lane == 0) {
-            while (*prog_prev < need + 1) __nanosleep(100);
-            __threadfence();
+            while (lf_ld_acquire(const_cast<const int *>(prog_prev)) < need + 1) __nanosleep(64);
         }
         __syncwarp();
     };
@@ -198,7 +187,7 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
             if (lane > 0) prevL = up;
         }
         if (valid) emit(lo, cur);
-        if (has_next && lane == 31) { __stcg(&bnd_next[lo], cur); __threadfence(); *prog_next = lo + 1; }
+        if (has_next && lane == 31) { __stcg(&bnd_next[lo], cur); lf_st_release(const_cast<int *>(prog_next), lo + 1); }
     }
 
     // ---- wavefront over the remaining rows in chunks of 32 steps (core:3365-3387 / :3550-3572) ----
@@ -276,9 +265,8 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
                 }
             }
             if (has_next && lane == 31) {      // rows <= lo + send - 31 of the last column are final
-                __threadfence();
                 const int done = lo + send - 31;
-                if (done > lo) *prog_next = min(done, g.row_end - 1) + 1;
+                if (done > lo) lf_st_release(const_cast<int *>(prog_next), min(done, g.row_end - 1) + 1);
             }
         }
         lf_cp_async_wait_all();

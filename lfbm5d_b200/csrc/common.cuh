@@ -41,3 +41,26 @@ struct LfWindow {
     unsigned proc[LF_MAXA];
     int      A;
 };
+
+__device__ __forceinline__ void lf_cp_async4(float *smem_dst, const float *gsrc)
+{
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void lf_cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;\n" ::: "memory");
+}
+
+
+// release/acquire flag accesses at GPU scope (producer/consumer hand-off between CTAs)
+__device__ __forceinline__ void lf_st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lf_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}

@@ -457,16 +457,19 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         // ---- gather (core:286-299): raw patches ----
         {
             const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
+            // asynchronous global->shared copies: all of a thread's loads are in flight at once
             for (int pa = sub; pa < npatch; pa += PPI) {
-                float xv = 0.f, ev = 0.f;
+                float *dx = &X[pa * PS + poff];
                 if (!szero[pa]) {
                     const unsigned src = sofs[pa] + tofs;
-                    xv = g.nsym[src];
-                    if (STEP == 2) ev = g.bsym[src];
+                    lf_cp_async4(dx, g.nsym + src);
+                    if (STEP == 2) lf_cp_async4(&E[pa * PS + poff], g.bsym + src);
+                } else {
+                    *dx = 0.f;
+                    if (STEP == 2) E[pa * PS + poff] = 0.f;
                 }
-                X[pa * PS + poff] = xv;
-                if (STEP == 2) E[pa * PS + poff] = ev;
             }
+            lf_cp_async_wait_all();
         }
         __syncthreads();
         // ---- 2-D spatial transform; patches that read as zeros stay zero under any of the transforms ----
@@ -587,31 +590,42 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
         for (int c = 0; c < C; ++c) { num[c] = g.numsym[pix + c * plane]; den[c] = g.densym[pix + c * plane]; }
     if (tid == 0) s_total = 0;
     __syncthreads();
-    const int yw0 = y0 + 2 * warp;      // this warp owns tile rows yw0, yw0 + 1
 
-    // add the listed patches in list order
+
+    // add the listed patches in list order; loads of four consecutive entries are issued before any of them is added
     auto flush = [&]() {
         const int cnt = s_total;
-        for (int i = 0; i < cnt; ++i) {
-            const unsigned yx = list[i].yx;
-            const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);
-            if (py > yw0 + 1 || py + k <= yw0) continue;          // warp-uniform: patch does not reach this warp's rows
-            const int dy = y - py, dx = x - px;
-            if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
-                const int pq = dy * k + dx;
-                const float kv = skaiser[pq];
-                const float *zp = g.zbuf + (size_t) list[i].zidx * k2 + pq;
-                float z[3];
+        for (int i0 = 0; i0 < cnt; i0 += 4) {
+            float z[4][3], kw[4][3];
+            bool on[4];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) z[c] = c < C ? zp[c * k2] : 0.f;
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u;
+                on[u] = false;
+                if (i < cnt) {
+                    const unsigned yx = list[i].yx;
+                    const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);
+                    const int dy = y - py, dx = x - px;
+                    if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
+                        on[u] = true;
+                        const int pq = dy * k + dx;
+                        const float kv = skaiser[pq];
+                        const float *zp = g.zbuf + (size_t) list[i].zidx * k2 + pq;
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    if (c < C) {
-                        const float kw = kv * list[i].w[c];
-                        num[c] += kw * z[c];
-                        den[c] += kw;
+                        for (int c = 0; c < 3; ++c) {
+                            z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
+                            kw[u][c] = kv * list[i].w[c];
+                        }
                     }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (on[u]) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (c < C) { num[c] += kw[u][c] * z[u][c]; den[c] += kw[u][c]; }
+                }
         }
         __syncthreads();
         if (tid == 0) s_total = 0;
