@@ -1,0 +1,118 @@
+// See lfbm5d_host.h. Error behaviour follows the reference's drivers: message on cout, EXIT_FAILURE (1).
+#include "lfbm5d_host.h"
+#include "lfbm5d_cuda.h"
+#include <cstdlib>
+#include <iostream>
+
+namespace {
+lfbm5d_ctx *context()
+{
+    static lfbm5d_ctx *ctx = nullptr;
+    if (!ctx) {
+        const char *dev = getenv("LFBM5D_DEVICE");
+        if (lfbm5d_create(&ctx, dev ? atoi(dev) : 0) != 0) {
+            std::cout << "lfbm5d: " << lfbm5d_last_error() << std::endl;
+            ctx = nullptr;
+        }
+    }
+    return ctx;
+}
+std::vector<float *> pointers(std::vector<std::vector<float> > &LF, const std::vector<unsigned> &mask, size_t each, bool resize)
+{
+    std::vector<float *> p(LF.size(), nullptr);
+    for (size_t st = 0; st < LF.size(); st++) {
+        if (st < mask.size() && mask[st]) {
+            if (resize && LF[st].size() != each) LF[st].resize(each);
+            p[st] = LF[st].data();
+        }
+    }
+    return p;
+}
+int check_sizes(const std::vector<std::vector<float> > &LF, const std::vector<unsigned> &mask, unsigned asize, size_t each, const char *what)
+{
+    if (LF.size() != asize || mask.size() != asize) {
+        std::cout << what << " should have awidth*aheight sub-aperture images." << std::endl;
+        return 1;
+    }
+    for (unsigned st = 0; st < asize; st++)
+        if (mask[st] && LF[st].size() != each) {
+            std::cout << what << ": SAI " << st << " does not have width*height*chnls samples." << std::endl;
+            return 1;
+        }
+    return 0;
+}
+} // namespace
+
+int run_bm5d_1st_step(const float sigma, const float lambdaHard5D, std::vector<std::vector<float> > &LF_noisy,
+                      std::vector<unsigned> &LF_SAI_mask, std::vector<std::vector<float> > &LF_basic, const unsigned ang_major,
+                      const unsigned awidth, const unsigned aheight, const unsigned anHard, const unsigned width,
+                      const unsigned height, const unsigned chnls, const unsigned NHard, const unsigned nSim, const unsigned nDisp,
+                      const unsigned kHard, const unsigned pHard, const bool useSD, const unsigned tau_2D, unsigned tau_4D,
+                      const unsigned tau_5D, const unsigned color_space, const unsigned nb_threads)
+{
+    lfbm5d_ctx *ctx = context();
+    if (!ctx) return EXIT_FAILURE;
+    const unsigned asize = awidth * aheight;
+    const size_t each = (size_t) width * height * chnls;
+    if (LF_basic.size() != asize) LF_basic.resize(asize);      // bm5d.cpp:129-130
+    if (check_sizes(LF_noisy, LF_SAI_mask, asize, each, "LF_noisy")) return EXIT_FAILURE;
+    lfbm5d_params p = { sigma, lambdaHard5D, ang_major, awidth, aheight, anHard, width, height, chnls, NHard, nSim, nDisp, kHard, pHard,
+                        useSD ? 1u : 0u, tau_2D, tau_4D, tau_5D, color_space, nb_threads };
+    std::vector<float *> n = pointers(LF_noisy, LF_SAI_mask, each, false), b = pointers(LF_basic, LF_SAI_mask, each, true);
+    if (lfbm5d_step1(ctx, &p, n.data(), LF_SAI_mask.data(), b.data()) != 0) {
+        std::cout << lfbm5d_last_error() << std::endl;
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
+int run_bm5d_2nd_step(const float sigma, std::vector<std::vector<float> > &LF_noisy, std::vector<unsigned> &LF_SAI_mask,
+                      std::vector<std::vector<float> > &LF_basic, std::vector<std::vector<float> > &LF_denoised,
+                      const unsigned ang_major, const unsigned awidth, const unsigned aheight, const unsigned anWien,
+                      const unsigned width, const unsigned height, const unsigned chnls, const unsigned NWien, const unsigned nSim,
+                      const unsigned nDisp, const unsigned kWien, const unsigned pWien, const bool useSD, const unsigned tau_2D,
+                      unsigned tau_4D, const unsigned tau_5D, const unsigned color_space, const unsigned nb_threads)
+{
+    lfbm5d_ctx *ctx = context();
+    if (!ctx) return EXIT_FAILURE;
+    const unsigned asize = awidth * aheight;
+    const size_t each = (size_t) width * height * chnls;
+    if (LF_denoised.size() != asize) LF_denoised.resize(asize);   // bm5d.cpp:823-824
+    if (check_sizes(LF_noisy, LF_SAI_mask, asize, each, "LF_noisy") || check_sizes(LF_basic, LF_SAI_mask, asize, each, "LF_basic"))
+        return EXIT_FAILURE;
+    lfbm5d_params p = { sigma, 0.0f, ang_major, awidth, aheight, anWien, width, height, chnls, NWien, nSim, nDisp, kWien, pWien,
+                        useSD ? 1u : 0u, tau_2D, tau_4D, tau_5D, color_space, nb_threads };
+    std::vector<float *> n = pointers(LF_noisy, LF_SAI_mask, each, false), b = pointers(LF_basic, LF_SAI_mask, each, false),
+                         d = pointers(LF_denoised, LF_SAI_mask, each, true);
+    if (lfbm5d_step2(ctx, &p, n.data(), b.data(), LF_SAI_mask.data(), d.data()) != 0) {
+        std::cout << lfbm5d_last_error() << std::endl;
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}
+
+int run_bm3d_LF(const float sigma, std::vector<std::vector<float> > &LF_noisy, std::vector<unsigned> &LF_SAI_mask,
+                std::vector<std::vector<float> > &LF_basic, std::vector<std::vector<float> > &LF_denoised, const unsigned width,
+                const unsigned height, const unsigned chnls, const unsigned nHard, const unsigned nWien, const unsigned kHard,
+                const unsigned kWien, const unsigned NHard, const unsigned NWien, const unsigned pHard, const unsigned pWien,
+                const bool useSD_h, const bool useSD_w, const unsigned tau_2D_hard, const unsigned tau_2D_wien,
+                const float lambdaHard3D, const unsigned color_space, const unsigned nb_threads, char *sub_img_name)
+{
+    (void) sub_img_name;
+    lfbm5d_ctx *ctx = context();
+    if (!ctx) return EXIT_FAILURE;
+    const unsigned asize = (unsigned) LF_noisy.size();
+    const size_t each = (size_t) width * height * chnls;
+    if (LF_basic.size() != asize) LF_basic.resize(asize);         // bm3d_LF.cpp:98-101
+    if (LF_denoised.size() != asize) LF_denoised.resize(asize);
+    if (check_sizes(LF_noisy, LF_SAI_mask, asize, each, "LF_noisy")) return EXIT_FAILURE;
+    lfbm3d_params p = { sigma, asize, width, height, chnls, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien,
+                        useSD_h ? 1u : 0u, useSD_w ? 1u : 0u, tau_2D_hard, tau_2D_wien, lambdaHard3D, color_space, nb_threads };
+    std::vector<float *> n = pointers(LF_noisy, LF_SAI_mask, each, false), b = pointers(LF_basic, LF_SAI_mask, each, true),
+                         d = pointers(LF_denoised, LF_SAI_mask, each, true);
+    if (lfbm3d_run(ctx, &p, n.data(), LF_SAI_mask.data(), b.data(), d.data()) != 0) {
+        std::cout << lfbm5d_last_error() << std::endl;
+        return EXIT_FAILURE;
+    }
+    return EXIT_SUCCESS;
+}

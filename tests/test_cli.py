@@ -1,0 +1,60 @@
+"""The LFBM5Ddenoising command line (same 37 positional arguments as the reference, README.md:50) end to end on the GPU:
+PNG in, PNG out, report file in the reference's format; and the C++ adapters with the reference's signatures."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import lfdata
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "lfbm5d_b200", "_lib")
+
+
+def test_cli_binary_and_host_library_exist():
+    """CPU-side check: the drivers are built and link against the C-ABI library only."""
+    for f in ("LFBM5Ddenoising", "liblfbm5d_host.so"):
+        assert os.path.exists(os.path.join(LIBDIR, f)), f
+    out = subprocess.check_output(["nm", "-D", "--defined-only", "-C", os.path.join(LIBDIR, "liblfbm5d_host.so")]).decode()
+    for sym in ("run_bm5d_1st_step", "run_bm5d_2nd_step", "run_bm3d_LF"):
+        assert sym + "(" in out
+    p = subprocess.run([os.path.join(LIBDIR, "LFBM5Ddenoising")], stdout=subprocess.PIPE)
+    assert p.returncode == 1 and b"usage: LFBM5Ddenoising LF_dir SAI_name" in p.stdout
+
+
+@pytest.mark.gpu
+def test_cli_readme_command(tmp_path):
+    from PIL import Image
+    clean = lfdata.synth_lf(3, 3, 64, 72)
+    src = tmp_path / "sourceLF"
+    for d in ("sourceLF", "noisyLF", "basicLF", "denoisedLF", "diffLF"):
+        (tmp_path / d).mkdir()
+    for s in range(3):
+        for t in range(3):
+            img = np.clip(np.floor(clean[s * 3 + t] + 0.5), 0, 255).astype(np.uint8).transpose(1, 2, 0)
+            Image.fromarray(img).save(str(src / ("SAI_%02d_%02d.png" % (s + 1, t + 1))))
+    report = tmp_path / "objectiveResults.txt"
+    # README.md:50 command line
+    args = [os.path.join(LIBDIR, "LFBM5Ddenoising"), str(src), "SAI", "_", "3", "3", "1", "1", "1", "1", "row", "25", "2.7",
+            str(tmp_path / "noisyLF"), str(tmp_path / "basicLF"), str(tmp_path / "denoisedLF"), str(tmp_path / "diffLF"),
+            "8", "18", "6", "16", "4", "id", "sadct", "haar", "0", "16", "18", "6", "8", "4", "dct", "sadct", "haar", "0",
+            "opp", "0", str(report)]
+    env = dict(os.environ, LFBM5D_SEED="20171016")
+    p = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+    out = p.stdout.decode()
+    assert p.returncode == 0, out[-2000:]
+    assert "Step 1 done in" in out and "Step 2 done in" in out and "THIS IS THE END" in out
+    for d in ("noisyLF", "basicLF", "denoisedLF", "diffLF"):
+        assert len(os.listdir(str(tmp_path / d))) == 9
+    txt = report.read_text()
+    vals = [float(x) for x in re.findall(r"-> Average PSNR \w+ = ([0-9.]+)", txt)]
+    assert len(vals) == 3 and vals[0] < vals[1] < vals[2] and vals[2] - vals[0] > 5.0
+    den = np.asarray(Image.open(str(tmp_path / "denoisedLF" / "SAI_02_02.png")), dtype=np.float32).transpose(2, 0, 1)
+    assert np.sqrt(np.mean((den - clean[4]) ** 2)) < 8.0
+    # second mode: no ground truth, noisy light field read back from disk (utilities_LF.cpp:1187)
+    args2 = list(args)
+    args2[1] = "none"
+    p = subprocess.run(args2, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+    assert p.returncode == 0 and b"Loading noisy LF elapsed time" in p.stdout
