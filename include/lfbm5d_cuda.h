@@ -89,6 +89,8 @@ int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, 
 int lfbm5d_step1_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, const unsigned *sai_mask, float *d_basic_out);
 int lfbm5d_step2_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io,
                         const unsigned *sai_mask, float *d_denoised_out);
+int lfbm3d_run_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy_io, const unsigned *sai_mask, float *d_basic_out,
+                      float *d_denoised_out);
 /* stop after this many window passes per step (0 = run to completion); for bounded measurements only */
 void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned max_passes);
 

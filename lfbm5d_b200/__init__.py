@@ -27,6 +27,15 @@ class Params(C.Structure):
                 ("color_space", C.c_uint), ("nb_threads", C.c_uint)]
 
 
+class Params3D(C.Structure):
+    """POD mirror of lfbm3d_params (include/lfbm5d_cuda.h)."""
+    _fields_ = [("sigma", C.c_float), ("asize", C.c_uint), ("width", C.c_uint), ("height", C.c_uint), ("chnls", C.c_uint),
+                ("nHard", C.c_uint), ("nWien", C.c_uint), ("kHard", C.c_uint), ("kWien", C.c_uint), ("NHard", C.c_uint),
+                ("NWien", C.c_uint), ("pHard", C.c_uint), ("pWien", C.c_uint), ("useSD_h", C.c_uint), ("useSD_w", C.c_uint),
+                ("tau_2D_hard", C.c_uint), ("tau_2D_wien", C.c_uint), ("lambdaHard3D", C.c_float), ("color_space", C.c_uint),
+                ("nb_threads", C.c_uint)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_ulonglong), ("window_passes", C.c_uint), ("ms_block_matching", C.c_float),
                 ("ms_groups", C.c_float), ("ms_aggregate", C.c_float), ("ms_other", C.c_float), ("ms_sat", C.c_float)]
@@ -34,7 +43,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset_stats", "lfbm5d_get_stats",
            "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
-           "lfbm5d_step2_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_bm_self",
+           "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_bm_self",
            "lfbm5d_debug_bm_stereo", "lfbm5d_debug_schedule"]
 
 _lib = None
@@ -58,6 +67,12 @@ def make_params(sigma, lam, aw, ah, an, width, height, chnls, N, nSim, nDisp, k,
                 color_space=OPP, ang_major=ROWMAJOR, useSD=0, nb_threads=1):
     return Params(sigma, lam, ang_major, aw, ah, an, width, height, chnls, N, nSim, nDisp, k, p, useSD, tau_2D, tau_4D,
                   tau_5D, color_space, nb_threads)
+
+
+def make_params3d(sigma, asize, width, height, chnls, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien, tau_2D_hard,
+                  tau_2D_wien, lambdaHard3D=2.7, color_space=OPP, nb_threads=1):
+    return Params3D(sigma, asize, width, height, chnls, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien, 0, 0, tau_2D_hard,
+                    tau_2D_wien, lambdaHard3D, color_space, nb_threads)
 
 
 def _fp(a):
@@ -137,6 +152,20 @@ class LFBM5D(object):
         if self.lib.lfbm5d_step2(self.ctx, C.byref(prm), self._ptrs(n), self._ptrs(b), _up(m), self._ptrs(out)) != 0:
             raise RuntimeError("lfbm5d_step2: " + self.error())
         return out, b, n
+
+    def bm3d(self, prm3, noisy, mask):
+        """run_bm3d_LF on host arrays [asize, C, H, W] -> (basic, denoised, noisy round-tripped)."""
+        n = np.ascontiguousarray(noisy, np.float32).copy()
+        basic, out = np.zeros_like(n), np.zeros_like(n)
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm3d_run(self.ctx, C.byref(prm3), self._ptrs(n), _up(m), self._ptrs(basic), self._ptrs(out)) != 0:
+            raise RuntimeError("lfbm3d_run: " + self.error())
+        return basic, out, n
+
+    def bm3d_device(self, prm3, d_noisy, mask, d_basic, d_out):
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm3d_run_device(self.ctx, C.byref(prm3), C.c_void_p(d_noisy), _up(m), C.c_void_p(d_basic), C.c_void_p(d_out)) != 0:
+            raise RuntimeError("lfbm3d_run_device: " + self.error())
 
     # -- device-resident entry points (raw device pointers, e.g. torch tensors' data_ptr()) -------
     def step1_device(self, prm, d_noisy, mask, d_basic):

@@ -167,7 +167,7 @@ int validate(const lfbm5d_params *p, int step)
     return 0;
 }
 
-int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau_4D)
+int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau_4D, bool bm3d = false)
 {
     static LfTables T;    // host staging (pageable); copy is synchronous with respect to the host
     memset(&T, 0, sizeof(T));
@@ -225,7 +225,8 @@ int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau
     for (unsigned c = 0; c < p->chnls; c++) {
         T.sigma2[c] = T.sigma[c] * T.sigma[c];
         for (int lg = 0; lg < 8; lg++)   // core:2306 (hw) and :2431 (haar, lg = 0)
-            T.thr[c][lg] = lambda * T.sigma[c] * sqrtf((float) (1u << lg)) * (float) (SQRT2_D);
+            T.thr[c][lg] = bm3d ? lambda * T.sigma[c] * sqrtf((float) (1u << lg))                       // bm3d.cpp:940
+                                : lambda * T.sigma[c] * sqrtf((float) (1u << lg)) * (float) (SQRT2_D);
     }
     for (int lg = 0; lg < 8; lg++) T.hadcoef[lg] = 1.0f / (float) (1u << lg);
     CK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -627,6 +628,94 @@ int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_nois
     return 0;
 }
 
+// out[c][i][j] = numsym / densym on the unpadded interior, without a zero guard (bm3d.cpp:476-477, :682-683)
+__global__ void k_ratio_crop(const float *__restrict__ numsym, const float *__restrict__ densym, float *__restrict__ out, int W, int H, int C, int n)
+{
+    const int wb = W + 2 * n, hb = H + 2 * n;
+    const size_t plane = (size_t) W * H, plane_b = (size_t) wb * hb, total = plane * C;
+    for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
+        const int c = (int) (t / plane);
+        const size_t px = t - (size_t) c * plane;
+        const int i = (int) (px / W), j = (int) (px - (size_t) i * W);
+        const size_t src = (size_t) c * plane_b + (size_t) (i + n) * wb + (j + n);
+        out[t] = numsym[src] / densym[src];
+    }
+}
+
+int validate_bm3d(const lfbm3d_params *p)
+{
+    if (!p) return fail("null params");
+    if (p->chnls != 1 && p->chnls != 3) return fail("chnls must be 1 or 3");
+    if (p->nHard != p->nWien) return fail("nHard must equal nWien (the reference passes the nHard-padded image to its 2nd step, bm3d.cpp:175)");
+    for (int s = 0; s < 2; s++) {
+        const unsigned k = s ? p->kWien : p->kHard, N = s ? p->NWien : p->NHard, t2 = s ? p->tau_2D_wien : p->tau_2D_hard;
+        if (k != 8 && k != 16) return fail("patch size must be 8 or 16 in this build");
+        if (N < 2 || N > LF_MAXN || (N & (N - 1))) return fail("N must be a power of two in [2, 32]");
+        if (t2 != LFBM5D_DCT && t2 != LFBM5D_BIOR) return fail("tau_2D must be dct or bior for BM3D");
+        if ((s ? p->pWien : p->pHard) == 0) return fail("processing step must be >= 1");
+    }
+    if (p->nHard + 1 < std::max(p->kHard, p->kWien)) return fail("nHard must be >= k - 1");
+    if (p->useSD_h || p->useSD_w) return fail("useSD weighting is not supported by this build");
+    if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");
+    if (p->width < 16 || p->height < 16) return fail("image smaller than a patch");
+    return 0;
+}
+
+// run_bm3d on every SAI (bm3d_LF.cpp:110-119 -> bm3d.cpp:86-287, nb_threads == 1): each SAI is the A = 1, no-disparity,
+// Hadamard case of a window pass with BM3D's thresholds. SAIs are independent, so step 1 runs for all of them before step 2
+// (one constant-table switch instead of 2 per SAI); results are identical to the per-SAI order.
+int bm3d_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy, const unsigned *mask, float *d_basic, float *d_out)
+{
+    if (validate_bm3d(p)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned asize = p->asize, C = p->chnls, W = p->width, H = p->height;
+    const size_t HW = (size_t) W * H, each = HW * C;
+    const bool docolor = C == 3 && p->color_space != LFBM5D_RGB;
+    if (ctx->mask.ensure(asize * 4) || ctx->num.ensure(each * 4) || ctx->den.ensure(each * 4)) return 1;
+    CK(cudaMemcpyAsync(ctx->mask.p, mask, asize * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (docolor) LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_noisy, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);   // bm3d.cpp:117
+    ctx->sched.clear();
+    for (int step = 1; step <= 2; step++) {
+        lfbm5d_params q{};
+        q.sigma = p->sigma; q.lambda = p->lambdaHard3D; q.ang_major = LFBM5D_ROWMAJOR; q.awidth = q.aheight = 1; q.an = 0;
+        q.width = W; q.height = H; q.chnls = C;
+        q.N = step == 1 ? p->NHard : p->NWien; q.nSim = step == 1 ? p->nHard : p->nWien; q.nDisp = 0;
+        q.k = step == 1 ? p->kHard : p->kWien; q.p = step == 1 ? p->pHard : p->pWien;
+        q.tau_2D = step == 1 ? p->tau_2D_hard : p->tau_2D_wien; q.tau_4D = LFBM5D_ID; q.tau_5D = LFBM5D_HADAMARD;
+        q.color_space = p->color_space; q.nb_threads = 1;
+        PassCfg pc;
+        if (make_passcfg(pc, step, &q, LFBM5D_ID)) return 1;
+        float st3[3];
+        if (estimate_sigma(p->sigma, st3, C, p->color_space)) return fail("unknown colour space");
+        pc.tauMatch = step == 1 ? (C == 1 ? 3.f : 1.f) * (st3[0] < 35.0f ? 2500 : 5000)      // bm3d.cpp:340
+                                : (st3[0] < 35.0f ? 400 : 3500);                             // bm3d.cpp:532
+        if (setup_tables(ctx, step, &q, LFBM5D_ID, true) || ensure_pass_buffers(ctx, pc) || upload_grid(ctx, pc)) return 1;
+        LfWindow win{};
+        win.A = 1; win.st[0] = 0; win.mask[0] = 1; win.proc[0] = 0;
+        float *dst = step == 1 ? d_basic : d_out;
+        for (unsigned st = 0; st < asize; st++) {
+            if (!mask[st]) continue;
+            CK(cudaMemsetAsync(ctx->num.p, 0, each * 4, ctx->stream));
+            CK(cudaMemsetAsync(ctx->den.p, 0, each * 4, ctx->stream));
+            LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) pc.wb * pc.hb), 256, 0, d_noisy + st * each,
+                   step == 2 ? d_basic + st * each : (const float *) nullptr, ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(),
+                   ctx->bsym.as<float>(), ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C,
+                   (int) pc.n);
+            if (run_pass(ctx, pc, win, 0)) return 1;
+            LAUNCH(ctx, k_ratio_crop, grid_for(ctx, each), 256, 0, ctx->numsym.as<float>(), ctx->densym.as<float>(), dst + st * each, (int) W,
+                   (int) H, (int) C, (int) pc.n);
+        }
+    }
+    if (docolor) {      // bm3d.cpp:269-274
+        LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_out, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 0);
+        LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_noisy, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 0);
+        LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_basic, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 0);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int upload_lf(lfbm5d_ctx *ctx, DevBuf &buf, float *const *host, const unsigned *mask, unsigned asize, size_t each)
 {
     if (buf.ensure(asize * each * 4)) return 1;
@@ -731,8 +820,23 @@ int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io
 int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out,
                float *const *denoised_out)
 {
-    (void) ctx; (void) p; (void) noisy_io; (void) sai_mask; (void) basic_out; (void) denoised_out;
-    return fail("lfbm3d_run: the per-SAI BM3D path is not implemented in this build");
+    if (!ctx || !noisy_io || !sai_mask || !basic_out || !denoised_out) return fail("null argument");
+    if (validate_bm3d(p)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const size_t each = (size_t) p->width * p->height * p->chnls;
+    if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, p->asize, each) || ctx->basic.ensure(p->asize * each * 4) ||
+        ctx->out.ensure(p->asize * each * 4)) return 1;
+    if (bm3d_device(ctx, p, ctx->noisy.as<float>(), sai_mask, ctx->basic.as<float>(), ctx->out.as<float>())) return 1;
+    if (download_lf(ctx, ctx->noisy, noisy_io, sai_mask, p->asize, each) || download_lf(ctx, ctx->basic, basic_out, sai_mask, p->asize, each))
+        return 1;
+    return download_lf(ctx, ctx->out, denoised_out, sai_mask, p->asize, each);
+}
+
+int lfbm3d_run_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy_io, const unsigned *sai_mask, float *d_basic_out,
+                      float *d_denoised_out)
+{
+    if (!ctx || !d_noisy_io || !sai_mask || !d_basic_out || !d_denoised_out) return fail("null argument");
+    return bm3d_device(ctx, p, d_noisy_io, sai_mask, d_basic_out, d_denoised_out);
 }
 
 unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries)

@@ -20,6 +20,7 @@
 #define SQRT2_INV_D 0.7071067811865475
 
 static int g_dct_mode = 0;
+static int g_bm3d = 0;      /* set while orc_run_bm3d_LF drives orc_pass: BM3D thresholds (bm3d.cpp:340, :532, :940) */
 static int g_threads = 0;
 void orc_set_dct_mode(int mode) { g_dct_mode = mode; }
 void orc_set_threads(int n) { g_threads = n; }
@@ -1017,7 +1018,8 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
         for (unsigned c = 0; c < C; c++) {
             const float sg = cx->sigma_table[c];
             float T;
-            if (cx->tau_5D == ORC_HAAR) T = cx->lambda * sg * (float) (SQRT2_D);
+            if (g_bm3d) T = cx->lambda * sg * sqrtf((float) nSx);                 /* bm3d.cpp:940 */
+            else if (cx->tau_5D == ORC_HAAR) T = cx->lambda * sg * (float) (SQRT2_D);
             else T = cx->lambda * sg * sqrtf((float) nSx) * (float) (SQRT2_D);
             for (unsigned st = 0; st < A; st++) {
                 if (sh.use_sadct && !sh.mask_dct[st]) continue;
@@ -1096,7 +1098,9 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
     if (asw > 1) orc_preProcess_4d_sadct(cx->cnsa, cx->cnisa, asw);
     cx->lambda = lambda;
     if (step == 1 && tau_2D == ORC_ID && tau_4D == ORC_DCT) cx->lambda = lambda / (float) (SQRT2_D);   /* core:206-207 */
-    const float tauMatch = (chnls == 1 ? 3.f : 1.f) * (cx->sigma_table[0] < 35.0f ? (step == 1 ? 3000 : 2000) : 5000);  /* core:146 / :915 */
+    float tauMatch = (chnls == 1 ? 3.f : 1.f) * (cx->sigma_table[0] < 35.0f ? (step == 1 ? 3000 : 2000) : 5000);  /* core:146 / :915 */
+    if (g_bm3d) tauMatch = step == 1 ? (chnls == 1 ? 3.f : 1.f) * (cx->sigma_table[0] < 35.0f ? 2500 : 5000)      /* bm3d.cpp:340 */
+                                     : (cx->sigma_table[0] < 35.0f ? 400 : 3500);                                /* bm3d.cpp:532 */
 
     unsigned *rows = (unsigned *) malloc(sizeof(unsigned) * (h_b + 2)), *cols = (unsigned *) malloc(sizeof(unsigned) * (w_b + 2));
     const unsigned nr = orc_ind_initialize(rows, h_b - k + 1, n, p), nc = orc_ind_initialize(cols, w_b - k + 1, n, p);
@@ -1389,20 +1393,55 @@ void orc_psnr(const float *a, const float *b, size_t n, float *psnr, float *rmse
     *psnr = 20.0f * log10f(255.0f / (*rmse));
 }
 
-/* BM3D path: see lfbm5d_oracle_bm3d section below (added with the LFBM3D kernels). */
+/* ------------------------------------------------------------------------------------------ */
+/* per-SAI BM3D (bm3d_LF.cpp:69-122 -> bm3d.cpp:86-287, nb_threads == 1): the A = 1, no-disparity,   */
+/* Hadamard specialisation of a window pass with BM3D's own thresholds                              */
+/* ------------------------------------------------------------------------------------------ */
+/* bm3d.cpp:1187-1330 is the self block matching with search radius = border */
 void orc_bm3d_bm(const float *img, unsigned width, unsigned height, unsigned kHW, unsigned NHW, unsigned nHW,
                  unsigned pHW, float tauMatch, unsigned *out_count, unsigned *out_idx, unsigned maxN)
 {
-    (void) img; (void) width; (void) height; (void) kHW; (void) NHW; (void) nHW; (void) pHW; (void) tauMatch;
-    (void) out_count; (void) out_idx; (void) maxN;
+    orc_bm_self(img, width, height, kHW, NHW, nHW, nHW, pHW, tauMatch, out_count, out_idx, maxN);
 }
+
 int orc_run_bm3d_LF(float sigma, float *noisy, const unsigned *mask, float *basic, float *denoised, unsigned asize,
                     unsigned width, unsigned height, unsigned chnls, unsigned nHard, unsigned nWien, unsigned kHard,
                     unsigned kWien, unsigned NHard, unsigned NWien, unsigned pHard, unsigned pWien,
                     unsigned tau_2D_hard, unsigned tau_2D_wien, float lambdaHard3D, unsigned color_space)
 {
-    (void) sigma; (void) noisy; (void) mask; (void) basic; (void) denoised; (void) asize; (void) width; (void) height; (void) chnls;
-    (void) nHard; (void) nWien; (void) kHard; (void) kWien; (void) NHard; (void) NWien; (void) pHard; (void) pWien;
-    (void) tau_2D_hard; (void) tau_2D_wien; (void) lambdaHard3D; (void) color_space;
-    return 3;   /* not restated yet */
+    if (nHard != nWien || NHard < 2 || NWien < 2) return 1;      /* bm3d.cpp:175 passes the nHard-padded buffers with nWien */
+    if ((tau_2D_hard != ORC_DCT && tau_2D_hard != ORC_BIOR) || (tau_2D_wien != ORC_DCT && tau_2D_wien != ORC_BIOR)) return 1;
+    const size_t each = (size_t) width * height * chnls;
+    const unsigned w_b = width + 2 * nHard, h_b = height + 2 * nHard;
+    const size_t each_b = (size_t) w_b * h_b * chnls;
+    float *nsym = (float *) malloc(sizeof(float) * each_b), *bsym = (float *) malloc(sizeof(float) * each_b);
+    float *num = (float *) malloc(sizeof(float) * each_b), *den = (float *) malloc(sizeof(float) * each_b);
+    const unsigned one = 1, zero = 0;
+    int rc = 0;
+    g_bm3d = 1;
+    for (unsigned st = 0; st < asize && rc == 0; st++) {
+        if (!mask[st]) continue;
+        float *nz = noisy + st * each, *bs = basic + st * each, *dn = denoised + st * each;
+        if (orc_color_space_transform(nz, color_space, width, height, chnls, 1)) { rc = 1; break; }      /* bm3d.cpp:117 */
+        orc_symetrize(nz, nsym, width, height, chnls, nHard);
+        memset(num, 0, sizeof(float) * each_b); memset(den, 0, sizeof(float) * each_b);
+        rc = orc_pass(1, sigma, lambdaHard3D, nsym, NULL, num, den, &one, &zero, 0, 1, w_b, h_b, chnls, nHard, 0, kHard, NHard, pHard,
+                      color_space, tau_2D_hard, ORC_ID, ORC_HADAMARD, NULL, NULL, NULL, NULL);
+        if (rc) break;
+        for (size_t t = 0; t < each_b; t++) num[t] = num[t] / den[t];                                    /* bm3d.cpp:476-477 */
+        orc_unsymetrize(bs, num, width, height, chnls, nHard);
+        orc_symetrize(bs, bsym, width, height, chnls, nHard);                                            /* bm3d.cpp:152-160 */
+        memset(num, 0, sizeof(float) * each_b); memset(den, 0, sizeof(float) * each_b);
+        rc = orc_pass(2, sigma, 0.0f, nsym, bsym, num, den, &one, &zero, 0, 1, w_b, h_b, chnls, nWien, 0, kWien, NWien, pWien,
+                      color_space, tau_2D_wien, ORC_ID, ORC_HADAMARD, NULL, NULL, NULL, NULL);
+        if (rc) break;
+        for (size_t t = 0; t < each_b; t++) num[t] = num[t] / den[t];                                    /* bm3d.cpp:682-683 */
+        orc_unsymetrize(dn, num, width, height, chnls, nWien);
+        orc_color_space_transform(dn, color_space, width, height, chnls, 0);                             /* bm3d.cpp:269-274 */
+        orc_color_space_transform(nz, color_space, width, height, chnls, 0);
+        orc_color_space_transform(bs, color_space, width, height, chnls, 0);
+    }
+    g_bm3d = 0;
+    free(nsym); free(bsym); free(num); free(den);
+    return rc;
 }

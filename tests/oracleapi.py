@@ -130,3 +130,14 @@ def run_step2(noisy, basic, mask, sigma, aw, ah, an, N, nSim, nDisp, k, p, tau2,
                              N, nSim, nDisp, k, p, tau2, tau4, tau5, cs, up(sched), A + 1, C.byref(ns), max_passes)
     assert rc == 0, rc
     return den, b, n, sched[:ns.value]
+
+
+def run_bm3d_lf(noisy, mask, sigma, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien, tau2h, tau2w, lam, cs=OPP):
+    A, Cn, H, W = noisy.shape
+    n = f32(noisy).copy()
+    basic = np.zeros_like(n)
+    den = np.zeros_like(n)
+    rc = lib().orc_run_bm3d_LF(C.c_float(sigma), fp(n), up(u32(mask)), fp(basic), fp(den), A, W, H, Cn, nHard, nWien, kHard, kWien,
+                               NHard, NWien, pHard, pWien, tau2h, tau2w, C.c_float(lam), cs)
+    assert rc == 0, rc
+    return basic, den, n

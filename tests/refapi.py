@@ -114,3 +114,14 @@ def precompute_bm_stereo(img1, img2, k, nHW, nDisp, tau, want_all=False):
                                         up(shape), up(allv) if want_all else None)
     assert rc == 0
     return first, shape, allv
+
+
+def run_bm3d_lf(noisy, mask, sigma, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien, tau2h, tau2w, lam, cs=OPP, nb_threads=1):
+    A, Cn, H, W = noisy.shape
+    n = f32(noisy).copy()
+    basic = np.zeros_like(n)
+    den = np.zeros_like(n)
+    rc = lib().ref_run_bm3d_LF(C.c_float(sigma), fp(n), up(u32(mask)), fp(basic), fp(den), A, W, H, Cn, nHard, nWien, kHard, kWien,
+                               NHard, NWien, pHard, pWien, 0, 0, tau2h, tau2w, C.c_float(lam), cs, nb_threads)
+    assert rc == 0
+    return basic, den, n

@@ -187,3 +187,14 @@ def test_full_run_multi_pass_bit_exact(oracle, ref):
     od, ob2, on2, sch = oracle.run_step2(on, ob, mask, 25.0, 5, 5, 1, 16, 18, 6, 8, 4, oracle.DCT, oracle.SADCT, oracle.HAAR)
     assert np.array_equal(rd, od) and np.array_equal(rb2, ob2) and np.array_equal(rn2, on2)
     assert oracle.psnr(od, clean)[0] > oracle.psnr(ob, clean)[0] > oracle.psnr(noisy, clean)[0] + 5
+
+
+def test_lfbm3d_bit_exact(oracle, ref):
+    """bm3d_LF path (config 4 parameters): A = 1 specialisation with BM3D's thresholds."""
+    clean = lfdata.synth_lf(2, 1, 36, 44)
+    noisy = oracle.add_noise(clean, 10.0)
+    mask = np.ones(2)
+    for (t2h, t2w) in ((ref.BIOR, ref.DCT), (ref.DCT, ref.BIOR)):
+        rb, rd, rn = ref.run_bm3d_lf(noisy, mask, 10.0, 16, 16, 8, 8, 16, 32, 3, 3, t2h, t2w, 2.7)
+        ob, od, on = oracle.run_bm3d_lf(noisy, mask, 10.0, 16, 16, 8, 8, 16, 32, 3, 3, t2h, t2w, 2.7)
+        assert np.array_equal(rb, ob) and np.array_equal(rd, od) and np.array_equal(rn, on)
