@@ -592,39 +592,42 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
     __syncthreads();
 
 
-    // add the listed patches in list order; loads of four consecutive entries are issued before any of them is added
+    // add the listed patches in list order; the loads of eight consecutive entries are issued before any of them is added
+    // (memory-level parallelism: only ~1/4 of the lanes are covered by a given patch)
+    const int tyx = (y - y0) * 16 + (x - x0);      // unused placeholder to keep per-thread constants together
+    (void) tyx;
     auto flush = [&]() {
         const int cnt = s_total;
-        for (int i0 = 0; i0 < cnt; i0 += 4) {
-            float z[4][3], kw[4][3];
-            bool on[4];
+        constexpr int U = 8;
+        for (int i0 = 0; i0 < cnt; i0 += U) {
+            float z[U][3], kv[U];
+            unsigned on = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int i = i0 + u;
-                on[u] = false;
                 if (i < cnt) {
                     const unsigned yx = list[i].yx;
-                    const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);
-                    const int dy = y - py, dx = x - px;
+                    const int dy = y - (int) (yx >> 16), dx = x - (int) (yx & 0xffffu);
                     if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
-                        on[u] = true;
+                        on |= 1u << u;
                         const int pq = dy * k + dx;
-                        const float kv = skaiser[pq];
+                        kv[u] = skaiser[pq];
                         const float *zp = g.zbuf + (size_t) list[i].zidx * k2 + pq;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
-                            kw[u][c] = kv * list[i].w[c];
-                        }
+                        for (int c = 0; c < 3; ++c) z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
                     }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (on[u]) {
+            for (int u = 0; u < U; ++u)
+                if (on & (1u << u)) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        if (c < C) { num[c] += kw[u][c] * z[u][c]; den[c] += kw[u][c]; }
+                        if (c < C) {
+                            const float kw = kv[u] * list[i0 + u].w[c];
+                            num[c] += kw * z[u][c];
+                            den[c] += kw;
+                        }
                 }
         }
         __syncthreads();

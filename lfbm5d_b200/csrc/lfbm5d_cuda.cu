@@ -431,6 +431,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     GroupArgs ga{};
     ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
     ga.pst = pst; ga.nc = nc;
+    // row padding removes the shared-memory bank conflicts of the 2-D passes (3 CTAs/SM without it measured slower)
     ga.RS = pc.tau_2D == LFBM5D_ID ? pc.k : pc.k + 1;
     ga.PS = pc.k * ga.RS;
     ga.tau_2D = pc.tau_2D; ga.tau_4D = pc.tau_4D; ga.tau_5D = pc.tau_5D;
