@@ -21,6 +21,8 @@ struct SatGeom {
     int nc;                 // number of reference-patch columns (self)
     const int *rowmap;      // [h] row -> reference row index or -1 (self)
     const int *colmap;      // [w]
+    int gp, nreg, rlast, nr;     // reference rows (self): lo + a*gp for a < nreg, plus rlast (index nr-1)
+    unsigned long long negzero2; // packed (-0.f, -0.f) supplied at run time (see lf_mul2)
 };
 // One offset plane: d(y,x) = (img2[y+oy][x+ox] - img1[y][x])^2, oy shared by the group.
 struct SatPlane {
@@ -30,8 +32,8 @@ struct SatPlane {
     float *out_mir;         // self: sums sampled at (ref - (mir_di, -mir_dc)) (pre-filled with 2*threshold)
     int    mir_di, mir_dc;
 };
-// Up to SAT_NW planes that share the two source images and the row offset: one CTA per (group, strip).
-#define SAT_NW 13
+// Up to 2*SAT_NW planes that share the two source images and the row offset: one CTA per (group, strip).
+#define SAT_NW 7          // warps per CTA; each warp sweeps two planes
 struct SatGroup {
     const float *img1, *img2;
     int oy, oxmin, nplanes, first_plane;
@@ -51,29 +53,62 @@ template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 // order so that a producer has always started before its consumer (no deadlock). Source rows of both images are
 // staged once per CTA with cp.async into two 128-row shared-memory rings (row stride 64 floats: the skewed reads
 // are bank-conflict free) and reused by all planes of the group; squared differences are formed on the fly.
+// ---- packed FP32x2 arithmetic (FADD2 / FMUL2 on sm_100): two planes per lane, IEEE per half ----
+__device__ __forceinline__ unsigned long long lf_pk(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void lf_upk(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long lf_add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long lf_sub2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Exact packed product. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (observed, CUDA 12.9) even with
+// -fmad=false — also when the product is written as fma(a, b, -0) with a literal -0 — which would change the rounding of
+// the recurrence. With the -0 addend supplied at run time (SatGeom::negzero2) ptxas cannot fold it: fma(a, b, -0) is the
+// exact product (round(a*b + -0) = round(a*b), +0 for a zero product) and stays separate from the following add.
+__device__ __forceinline__ unsigned long long lf_mul2(unsigned long long a, unsigned long long b, unsigned long long negzero)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
+    return r;
+}
+
+// Summed-area planes, v3. As v2, with TWO planes per lane (column offsets ox and ox+1 of the same group): the img1
+// operand is shared, the img2 operands are adjacent ring entries, and all floating-point work of the step runs as packed
+// FP32x2 instructions (bit-identical per half), which halves the issue slots of the issue-bound inner loop.
 template <bool SELF, int K>
-__global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
+__global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
                                                           int ngroups, float *bnd, int *progress, int *ticket_counter)
 {
     extern __shared__ float s_dyn[];
     // source-row rings of img1 / img2: 128 rows + K mirror rows (slot s < K is also stored at s + 128, so that the
     // row K below any slot is always at slot + K without wrapping)
     float *R1 = s_dyn, *R2 = s_dyn + (128 + K) * 64;
-    int *s_maps = reinterpret_cast<int *>(s_dyn + 2 * (128 + K) * 64);   // SELF: rowmap[h] then colmap[w]
     __shared__ int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     if (tid == 0) s_ticket = atomicAdd(ticket_counter, 1);
-    if (SELF) {
-        for (int t = tid; t < g.h; t += blockDim.x) s_maps[t] = g.rowmap[t];
-        for (int t = tid; t < g.w; t += blockDim.x) s_maps[g.h + t] = g.colmap[t];
-    }
     __syncthreads();
     const int strip = s_ticket / ngroups, gi = s_ticket - strip * ngroups;
     const SatGroup G = groups[gi];
-    const bool hasplane = warp < G.nplanes;
-    const int pid = G.first_plane + (hasplane ? warp : 0);
-    const SatPlane P = planes[pid];
+    const bool hasplane = 2 * warp < G.nplanes;
+    const bool hasB = 2 * warp + 1 < G.nplanes;
+    const int pid = G.first_plane + (hasplane ? 2 * warp : 0);        // plane A; plane B = pid + 1 (A again when absent)
+    const SatPlane PA = planes[pid], PB = planes[hasB ? pid + 1 : pid];
     const int w = g.w, h = g.h, lo = g.lo;
     constexpr int k = K;
     const int W = g.col_end - lo, Hh = g.row_end - lo;
@@ -83,14 +118,15 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
     const int lastlane = min(31, W - 1 - (strip << 5));
     const bool has_next = strip + 1 < g.nstrips;
     const int xb1 = c0 - 1, xb2 = c0 - 1 + G.oxmin;
-    const int oxo = P.ox - G.oxmin;                    // column shift of this plane inside the img2 ring
-    const int ymax = min(g.row_end - 1 + k - 1, h - 1);   // last source row ever needed
-    float *bnd_prev = bnd + ((size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0)) * h;
-    float *bnd_next = bnd + ((size_t) pid * g.nstrips + strip) * h;
-    volatile int *prog_prev = progress + (size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0);
-    volatile int *prog_next = progress + (size_t) pid * g.nstrips + strip;
+    const int oxo = PA.ox - G.oxmin;                   // column shift of plane A inside the img2 ring (plane B: +1)
+    const int ymax = min(g.row_end - 1 + k - 1, h - 1);
+    const size_t pstride = (size_t) g.nstrips * h;
+    float *bnd_prev = bnd + (size_t) pid * pstride + (size_t) (strip > 0 ? strip - 1 : 0) * h;
+    float *bnd_next = bnd + (size_t) pid * pstride + (size_t) strip * h;
+    const size_t bB = hasB ? pstride : 0;              // offset from plane A's boundary column to plane B's
+    const int *prog_prev = progress + (size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0);
+    int *prog_next = progress + (size_t) pid * g.nstrips + strip;
 
-    // rows [y0, y1] of both images into the rings (all threads)
     auto load_rows = [&](int y0, int y1) {
         if (y1 > ymax) y1 = ymax;
         const int n = (y1 - y0 + 1) * 128;
@@ -113,40 +149,52 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
             }
         }
     };
-    // squared difference at source row y, ring column slot cs (= x - xb1) — prologue / first-column paths only
-    auto dval = [&](int y, int cs) -> float {
+    // squared difference of plane `pl` (0 = A, 1 = B) at source row y, ring column slot cs — cold paths only
+    auto dval = [&](int pl, int y, int cs) -> float {
         const float a = R1[(y & 127) * 64 + cs];
-        const float b = R2[((y + G.oy) & 127) * 64 + cs + oxo];
+        const float b = R2[((y + G.oy) & 127) * 64 + cs + oxo + pl];
         const float df = b - a;
         float v = df * df;
         if (SELF) { if (y >= g.ylim || xb1 + cs >= g.xlim) v = 0.f; }
         return v;
     };
-    // per-lane constants of the sampled outputs (self) / the skewed output pointer (stereo)
-    int colb = -1, colb2 = -1;
-    float *outp = nullptr;
+    // per-lane constants of the sampled outputs (self) / the skewed output pointers (stereo)
+    int colb = -1, colbA2 = -1, colbB2 = -1;
+    float *outA = nullptr, *outB = nullptr;
     if (SELF) {
-        if (j < w) colb = s_maps[h + j];
-        const int jr = j - P.mir_dc;
-        if (P.mir_di > 0 && jr >= 0 && jr < w) colb2 = s_maps[h + jr];
+        if (j < w) colb = g.colmap[j];
+        const int jA = j - PA.mir_dc, jB = j - PB.mir_dc;
+        if (PA.mir_di > 0 && jA >= 0 && jA < w) colbA2 = g.colmap[jA];
+        if (PB.mir_di > 0 && jB >= 0 && jB < w && hasB) colbB2 = g.colmap[jB];
     } else {
-        outp = P.out_skew + ((size_t) strip * g.SR) * 32 + lane;      // + sidx*32, sidx = (i - lo) + lane
+        outA = PA.out_skew + ((size_t) strip * g.SR) * 32 + lane;      // + sidx*32, sidx = (i - lo) + lane
+        outB = PB.out_skew + ((size_t) strip * g.SR) * 32 + lane;
     }
-    auto emit = [&](int i, float v) {     // s(i, j) of this lane
-        if (SELF) {
-            const int a = s_maps[i];
-            if (a >= 0 && colb >= 0) P.out_at[a * g.nc + colb] = v;
-            if (colb2 >= 0) {
-                const int a2 = s_maps[i + P.mir_di];
-                if (a2 >= 0) P.out_mir[a2 * g.nc + colb2] = v;
-            }
-        } else {
-            outp[(size_t) ((i - lo) + lane) * 32] = v;
+    // reference-row index of row i (or -1), by arithmetic (self planes)
+    auto row_index = [&](int i) -> int {
+        const int d = i - lo;
+        if (i == g.rlast) return g.nr - 1;
+        if (d >= 0 && d % g.gp == 0 && d / g.gp < g.nreg) return d / g.gp;
+        return -1;
+    };
+    auto emit_self = [&](int a, int a2, float vA, float vB) {     // a / a2: reference-row index of rows i and i + mir_di
+        if (a >= 0 && colb >= 0) { PA.out_at[a * g.nc + colb] = vA; if (hasB) PB.out_at[a * g.nc + colb] = vB; }
+        if (a2 >= 0) {
+            if (colbA2 >= 0) PA.out_mir[a2 * g.nc + colbA2] = vA;
+            if (colbB2 >= 0) PB.out_mir[a2 * g.nc + colbB2] = vB;
+        }
+    };
+    auto emit = [&](int i, float vA, float vB) {     // cold paths (first row / first column)
+        if (SELF) emit_self(row_index(i), PA.mir_di > 0 ? row_index(i + PA.mir_di) : -1, vA, vB);
+        else {
+            const size_t o = (size_t) ((i - lo) + lane) * 32;
+            outA[o] = vA;
+            if (hasB) outB[o] = vB;
         }
     };
     auto wait_prev = [&](int need) {      // producer strip has published rows <= need (flag holds row + 1)
         if (lane == 0) {
-            while (lf_ld_acquire(const_cast<const int *>(prog_prev)) < need + 1) __nanosleep(64);
+            while (lf_ld_acquire(prog_prev) < need + 1) __nanosleep(64);
         }
         __syncwarp();
     };
@@ -156,38 +204,43 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
     lf_cp_async_wait_all();
     __syncthreads();
 
-    float cur = 0.f, prevL = 0.f;
+    float curv[2] = { 0.f, 0.f }, prevv[2] = { 0.f, 0.f };
     if (hasplane) {
         // first row of the strip (core:3345-3362 / :3530-3547): s(lo, j) = s(lo, j-1) + sum_p (d[lo+p][j-1+k] - d[lo+p][j-1]),
         // the differences formed in parallel (lane p), the additions strictly in order
-        float left = 0.f;
-        int l0 = 0;
-        if (strip == 0) {      // first patch: sequential sum over its k*k squared differences
-            float v = 0.0f;
-            for (int p = 0; p < k; ++p) {
-                const float dv = lane < k ? dval(lo + p, 1 + lane) : 0.f;
-                for (int t = 0; t < k; ++t) v += __shfl_sync(FULL, dv, t);
+        if (strip > 0) wait_prev(lo);
+        for (int pl = 0; pl < 2; ++pl) {
+            float left = 0.f, cur = 0.f, prevL = 0.f;
+            int l0 = 0;
+            if (strip == 0) {      // first patch: sequential sum over its k*k squared differences
+                float v = 0.0f;
+                for (int p = 0; p < k; ++p) {
+                    const float dv = lane < k ? dval(pl, lo + p, 1 + lane) : 0.f;
+                    for (int t = 0; t < k; ++t) v += __shfl_sync(FULL, dv, t);
+                }
+                left = v; l0 = 1;
+                if (lane == 0) cur = v;
+            } else {
+                left = __ldcg(&bnd_prev[lo + (pl ? bB : 0)]);
+                prevL = left;       // lane 0: s(lo, c0-1)
             }
-            left = v; l0 = 1;
-            if (lane == 0) cur = v;
-        } else {
-            wait_prev(lo);
-            left = __ldcg(&bnd_prev[lo]);
-            prevL = left;       // lane 0: s(lo, c0-1)
-        }
-        for (int l = l0; l <= lastlane; ++l) {
-            float s = left;
-            const float e = lane < k ? dval(lo + lane, l + k) - dval(lo + lane, l) : 0.f;
-            for (int t = 0; t < k; ++t) s += __shfl_sync(FULL, e, t);
-            if (lane == l) cur = s;
-            left = s;
-        }
-        {
+            for (int l = l0; l <= lastlane; ++l) {
+                float s = left;
+                const float e = lane < k ? dval(pl, lo + lane, l + k) - dval(pl, lo + lane, l) : 0.f;
+                for (int t = 0; t < k; ++t) s += __shfl_sync(FULL, e, t);
+                if (lane == l) cur = s;
+                left = s;
+            }
             const float up = __shfl_up_sync(FULL, cur, 1);
             if (lane > 0) prevL = up;
+            curv[pl] = cur; prevv[pl] = prevL;
         }
-        if (valid) emit(lo, cur);
-        if (has_next && lane == 31) { __stcg(&bnd_next[lo], cur); lf_st_release(const_cast<int *>(prog_next), lo + 1); }
+        if (valid) emit(lo, curv[0], curv[1]);
+        if (has_next && lane == 31) {
+            __stcg(&bnd_next[lo], curv[0]);
+            if (hasB) __stcg(&bnd_next[lo + bB], curv[1]);
+            lf_st_release(prog_next, lo + 1);
+        }
     }
 
     // ---- wavefront over the remaining rows in chunks of 32 steps (core:3365-3387 / :3550-3572) ----
@@ -204,37 +257,65 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
     // lane is active at steps s in [lane + 1, lane + Hh - 1]
     const unsigned s_first = (valid && !skip0) ? (unsigned) (lane + 1) : 0x40000000u;
     const unsigned s_span = (unsigned) (Hh - 1);
-    float *bptr = bnd_next + (lo - lane);          // bptr[s] = bnd_next[i]
-    auto step_general = [&](int s, float Lsh, float bL) {
+    const bool bstore = has_next && lane == 31;
+    float *bpA = bnd_next + (lo - lane) + 1, *bpB = bpA + bB;       // running: bnd_next[i] of the current step
+    float *opA = outA + 32, *opB = outB + 32;                       // running: skewed output slot of the current step
+    // reference-row counters (self): phase and index of rows i and i + mir_di, advanced with the step
+    int ph1 = 0, ai1 = 0, ph2 = 0, ai2 = 0;
+    if (SELF) {
+        const int v1 = 1 - lane + 64 * g.gp, v2 = v1 + PA.mir_di;
+        ph1 = v1 % g.gp; ai1 = v1 / g.gp - 64;
+        ph2 = v2 % g.gp; ai2 = v2 / g.gp - 64;
+    }
+    const unsigned long long nz2 = g.negzero2;
+    unsigned long long cur2 = lf_pk(curv[0], curv[1]), prevL2 = lf_pk(prevv[0], prevv[1]);
+    auto step_general = [&](int s, unsigned long long Lin2) {
         if ((unsigned) s - s_first < s_span) {
             const unsigned a1 = sb1 + ro1, a2 = sb2 + ro2;
-            float t1 = lf_lds<K * 256 + K * 4>(a2) - lf_lds<K * 256 + K * 4>(a1);
-            float t2 = lf_lds<K * 256>(a2) - lf_lds<K * 256>(a1);
-            float t3 = lf_lds<K * 4>(a2) - lf_lds<K * 4>(a1);
-            float t4 = lf_lds<0>(a2) - lf_lds<0>(a1);
-            t1 *= t1; t2 *= t2; t3 *= t3; t4 *= t4;
-            const int i = lo + s - lane;
+            const float aNK = lf_lds<K * 256 + K * 4>(a1), aN0 = lf_lds<K * 256>(a1), aOK = lf_lds<K * 4>(a1), aO0 = lf_lds<0>(a1);
+            unsigned long long t1 = lf_sub2(lf_pk(lf_lds<K * 256 + K * 4>(a2), lf_lds<K * 256 + K * 4 + 4>(a2)), lf_pk(aNK, aNK));
+            unsigned long long t2 = lf_sub2(lf_pk(lf_lds<K * 256>(a2), lf_lds<K * 256 + 4>(a2)), lf_pk(aN0, aN0));
+            unsigned long long t3 = lf_sub2(lf_pk(lf_lds<K * 4>(a2), lf_lds<K * 4 + 4>(a2)), lf_pk(aOK, aOK));
+            unsigned long long t4 = lf_sub2(lf_pk(lf_lds<0>(a2), lf_lds<4>(a2)), lf_pk(aO0, aO0));
+            t1 = lf_mul2(t1, t1, nz2); t2 = lf_mul2(t2, t2, nz2); t3 = lf_mul2(t3, t3, nz2); t4 = lf_mul2(t4, t4, nz2);
             if (SELF) {
-                const bool rowz = i + k - 1 >= g.ylim;
-                if (rowz || colz) t1 = 0.f;
-                if (rowz) t2 = 0.f;
-                if (colz) t3 = 0.f;
+                const bool rowz = lo + s - lane + k - 1 >= g.ylim;
+                if (rowz || colz) t1 = 0ull;
+                if (rowz) t2 = 0ull;
+                if (colz) t3 = 0ull;
             }
-            const float L = lane == 0 ? bL : Lsh;
-            float nv = L + cur;
-            nv = nv - prevL;
-            nv = nv + t1;
-            nv = nv - t2;
-            nv = nv - t3;
-            nv = nv + t4;
-            prevL = L;
-            cur = nv;
-            emit(i, nv);
-            if (has_next && lane == 31) __stcg(&bptr[s], nv);
+            unsigned long long nv = lf_add2(Lin2, cur2);
+            nv = lf_sub2(nv, prevL2);
+            nv = lf_add2(nv, t1);
+            nv = lf_sub2(nv, t2);
+            nv = lf_sub2(nv, t3);
+            nv = lf_add2(nv, t4);
+            prevL2 = Lin2;
+            cur2 = nv;
+            float vA, vB;
+            lf_upk(nv, vA, vB);
+            if (SELF) {
+                const int i = lo + s - lane;
+                const int a = (i == g.rlast) ? g.nr - 1 : ((ph1 == 0 && ai1 < g.nreg) ? ai1 : -1);
+                const int a2 = (i + PA.mir_di == g.rlast) ? g.nr - 1 : ((ph2 == 0 && ai2 < g.nreg) ? ai2 : -1);
+                if ((a >= 0) | (a2 >= 0)) emit_self(a, PA.mir_di > 0 ? a2 : -1, vA, vB);
+            } else {
+                *opA = vA;
+                if (hasB) *opB = vB;
+            }
+            if (bstore) { __stcg(bpA, vA); if (hasB) __stcg(bpB, vB); }
         }
         ro1 = (ro1 + 256u) & 32767u;
         ro2 = (ro2 + 256u) & 32767u;
+        ++bpA; ++bpB;
+        if (SELF) {
+            if (++ph1 == g.gp) { ph1 = 0; ++ai1; }
+            if (++ph2 == g.gp) { ph2 = 0; ++ai2; }
+        } else { opA += 32; opB += 32; }
     };
+    // per-warp staging of the 32 boundary pairs of a chunk (strip > 0): lane 0 reads one pair per step
+    __shared__ unsigned long long s_bnd[SAT_NW][32];
+    const unsigned sbn = (unsigned) __cvta_generic_to_shared(&s_bnd[warp][0]);
     for (int q = 0; q < nchunks; ++q) {
         // stage the source rows of the next chunk while this one runs
         load_rows(lo + 32 * (q + 1) + k, lo + 32 * (q + 1) + 32 + k - 1);
@@ -244,29 +325,35 @@ __global__ void __launch_bounds__(SAT_NW * 32, 2) k_sat2(SatGeom g, const SatGro
                 const int rlast = min(lo + 32 * q + 32, g.row_end - 1);
                 wait_prev(rlast);
                 const int r = lo + 32 * q + 1 + lane;
-                const float bchunk = r < g.row_end ? __ldcg(&bnd_prev[r]) : 0.f;
-                for (int s = 32 * q + 1; s <= send; ++s) {
-                    const float Lsh = __shfl_up_sync(FULL, cur, 1);
-                    const float bL = __shfl_sync(FULL, bchunk, (s - 1) & 31);
-                    step_general(s, Lsh, bL);
+                s_bnd[warp][lane] = r < g.row_end ? lf_pk(__ldcg(&bnd_prev[r]), __ldcg(&bnd_prev[r + bB])) : 0ull;
+                __syncwarp();
+                unsigned bo = sbn;
+                for (int s = 32 * q + 1; s <= send; ++s, bo += 8) {
+                    unsigned long long Lin2 = __shfl_up_sync(FULL, cur2, 1);
+                    if (lane == 0) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(Lin2) : "r"(bo));
+                    step_general(s, Lin2);
                 }
+                __syncwarp();
             } else {
                 for (int s = 32 * q + 1; s <= send; ++s) {
-                    const float Lsh = __shfl_up_sync(FULL, cur, 1);
+                    const unsigned long long Lsh2 = __shfl_up_sync(FULL, cur2, 1);
                     // first column (core:3367-3372): differences by lanes q < k, additions in order by lane 0
                     const int i0 = lo + s;
                     if (i0 < g.row_end) {
-                        float sum = cur;      // only lane 0's value is used
-                        const float e = lane < k ? dval(i0 - 1 + k, 1 + lane) - dval(i0 - 1, 1 + lane) : 0.f;
-                        for (int t = 0; t < k; ++t) sum += __shfl_sync(FULL, e, t);
-                        if (lane == 0) { cur = sum; emit(i0, sum); }
+                        float cA, cB;
+                        lf_upk(cur2, cA, cB);
+                        float sumA = cA, sumB = cB;      // only lane 0's values are used
+                        const float eA = lane < k ? dval(0, i0 - 1 + k, 1 + lane) - dval(0, i0 - 1, 1 + lane) : 0.f;
+                        const float eB = lane < k ? dval(1, i0 - 1 + k, 1 + lane) - dval(1, i0 - 1, 1 + lane) : 0.f;
+                        for (int t = 0; t < k; ++t) { sumA += __shfl_sync(FULL, eA, t); sumB += __shfl_sync(FULL, eB, t); }
+                        if (lane == 0) { cur2 = lf_pk(sumA, sumB); emit(i0, sumA, sumB); }
                     }
-                    step_general(s, Lsh, 0.f);
+                    step_general(s, Lsh2);
                 }
             }
-            if (has_next && lane == 31) {      // rows <= lo + send - 31 of the last column are final
+            if (bstore) {      // rows <= lo + send - 31 of the last column are final
                 const int done = lo + send - 31;
-                if (done > lo) lf_st_release(const_cast<int *>(prog_next), min(done, g.row_end - 1) + 1);
+                if (done > lo) lf_st_release(prog_next, min(done, g.row_end - 1) + 1);
             }
         }
         lf_cp_async_wait_all();

@@ -332,11 +332,11 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     std::vector<int> stereo_sai;
     const float *ref0 = est0 + (size_t) pst * plane;
     for (int di = 0; di < (nself ? (int) pc.nSim + 1 : 0); di++)
-        for (int djx0 = 0; djx0 < Ns; djx0 += SAT_NW) {
+        for (int djx0 = 0; djx0 < Ns; djx0 += 2 * SAT_NW) {
             SatGroup G{};
             G.img1 = ref0; G.img2 = ref0; G.oy = di; G.oxmin = djx0 - (int) pc.nSim;      // core:3331: dk = di*w + djx - nSim
             G.first_plane = (int) planes.size();
-            for (int djx = djx0; djx < std::min(Ns, djx0 + SAT_NW); djx++) {
+            for (int djx = djx0; djx < std::min(Ns, djx0 + 2 * SAT_NW); djx++) {
                 SatPlane P{};
                 const int ddk = di * Ns + djx;
                 P.ox = djx - (int) pc.nSim;
@@ -387,7 +387,11 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n;
         g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.SR = 0;
         g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
-        const size_t smem = 2 * (128 + pc.k) * 64 * 4 + (size_t) (pc.hb + pc.wb) * 4;
+        g.gp = pc.p; g.nr = nr; g.rlast = pc.rows.back();
+        g.nreg = 0;      // rows produced by the regular stride of ind_initialize (utilities.cpp:697-712)
+        for (unsigned ind = pc.n; ind < pc.hb - pc.k + 1 - pc.n; ind += pc.p) g.nreg++;
+        g.negzero2 = 0x8000000080000000ull;
+        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
         auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
         CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         kfn<<<nself_groups * self_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>(), ctx->satplanes.as<SatPlane>(),
@@ -398,6 +402,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         SatGeom g{};
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
         g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
+        g.gp = 1; g.negzero2 = 0x8000000080000000ull;
         const size_t smem = 2 * (128 + pc.k) * 64 * 4;
         const int ngroups = (int) groups.size() - nself_groups;
         auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
