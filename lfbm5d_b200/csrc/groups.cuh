@@ -547,6 +547,152 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Register-resident variant for tau_2D = id, k = 16, step 1 (configs 1, 3, 5 of BASELINE.json): thread <-> pixel position
+// of the patch, the N x 9 samples of that position across the group live in registers through the angular DCT, the Haar
+// transform along the similar patches, the hard threshold and both inverses. No shared-memory staging, all gathers of a
+// thread in flight at once, one block reduction per channel for the weight. Same arithmetic as k_groups (bit-identical).
+// ------------------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const unsigned *sofs, const unsigned char *szero, const GroupShape &sh,
+                                                     bool use_sadct, unsigned tofs, int c, int lg, float *zdst, int k2)
+{
+    constexpr int A = 9;
+    float x[NS][A];
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+        for (int st = 0; st < A; ++st) {
+            const int pa = n * A + st;
+            x[n][st] = szero[pa] ? 0.f : __ldg(g.nsym + sofs[pa] + tofs);
+        }
+    if (g.tau_4D != 4) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            if (use_sadct) {
+                float u[A];
+#pragma unroll
+                for (int st = 0; st < A; ++st) u[st] = x[n][st];
+                lf_sadct_fwd(u, sh, 3);
+#pragma unroll
+                for (int st = 0; st < A; ++st) x[n][st] = u[st];
+            } else lf_dct4_fwd<3>(x[n]);
+        }
+    }
+    float wpart = 0.f;
+    const bool haar = g.tau_5D == 9;
+    const float T = haar ? c_tab.thr[c][0] : c_tab.thr[c][lg];
+#pragma unroll
+    for (int st = 0; st < A; ++st) {
+        float v[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) v[n] = x[n][st];
+        if (NS > 1) { if (haar) lf_haar_fwd<NS>(v); else lf_hadamard<NS>(v); }
+        if (!use_sadct || sh.mask_dct[st]) {
+#pragma unroll
+            for (int n = 0; n < NS; ++n) { if (fabsf(v[n]) > T) wpart += 1.0f; else v[n] = 0.0f; }
+        }
+        if (NS > 1) {
+            if (haar) lf_haar_inv<NS>(v);
+            else {
+                lf_hadamard<NS>(v);
+                const float hc = c_tab.hadcoef[lg];
+#pragma unroll
+                for (int n = 0; n < NS; ++n) v[n] *= hc;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) x[n][st] = v[n];
+    }
+    if (g.tau_4D != 4) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            if (use_sadct) {
+                float u[A];
+#pragma unroll
+                for (int st = 0; st < A; ++st) u[st] = x[n][st];
+                lf_sadct_inv(u, sh, 3);
+#pragma unroll
+                for (int st = 0; st < A; ++st) x[n][st] = u[st];
+            } else lf_dct4_inv<3>(x[n]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+        for (int st = 0; st < A; ++st) zdst[((n * A + st) * g.C + c) * k2] = x[n][st];
+    return wpart;
+}
+
+__global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
+{
+    __shared__ GroupShape sh;
+    __shared__ float red[8];
+    __shared__ unsigned sofs[LF_MAXN * LF_MAXA];
+    __shared__ unsigned char szero[LF_MAXN * LF_MAXA];
+    constexpr int A = 9, k = 16, k2 = 256;
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x;
+    const int w = g.w;
+    const unsigned plane = (unsigned) g.w * (unsigned) g.h;
+    const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
+    const int nSx = (int) g.bm_count[r];
+    const int lg = 31 - __clz(nSx);
+    const int pq = tid, p = pq >> 4, q = pq & 15;
+    const int npatch = nSx * A;
+    for (int t = tid; t < npatch; t += 256) {
+        const int n = t / A, st = t - n * A;
+        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
+        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
+        sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv;
+        szero[t] = (!g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k) ? 1 : 0;
+        g.spos[((size_t) r * g.N + n) * A + st] = pv;
+    }
+    if (tid == 0) {
+        unsigned size = 0;
+        for (int st = 0; st < A; ++st) {
+            const unsigned m = (st == g.pst) ? 1u : (g.win.mask[st] ? (unsigned) g.shape[(size_t) st * plane + k_r] : 0u);
+            sh.mask[st] = m; size += m;
+            sh.idx[st] = 0; sh.idx_col[st] = 0; sh.mask_dct[st] = 0;
+        }
+        sh.use_sadct = (g.tau_4D == 6) && (size != (unsigned) A);
+        if (g.tau_4D == 6) {
+            unsigned mask_col[LF_MAXA];
+            for (int st = 0; st < A; ++st) mask_col[st] = 0;
+            for (int s = 0; s < 3; ++s) {
+                unsigned rr = 0;
+                for (int t = 0; t < 3; ++t) if (sh.mask[s * 3 + t]) sh.idx[s * 3 + rr++] = t;
+                sh.row_size[s] = rr;
+                for (unsigned t = 0; t < rr; ++t) mask_col[s * 3 + t] = 1;
+            }
+            for (int t = 0; t < 3; ++t) {
+                unsigned rr = 0;
+                for (int s = 0; s < 3; ++s) if (mask_col[s * 3 + t]) sh.idx_col[(rr++) * 3 + t] = s;
+                sh.col_size[t] = rr;
+                for (unsigned s = 0; s < rr; ++s) sh.mask_dct[s * 3 + t] = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < A)
+        g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
+    const bool use_sadct = sh.use_sadct != 0;
+    float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
+    for (int c = 0; c < g.C; ++c) {
+        const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
+        float wpart;
+        switch (nSx) {
+            case 1:  wpart = lf_group_id_channel<1>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
+            case 2:  wpart = lf_group_id_channel<2>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
+            case 4:  wpart = lf_group_id_channel<4>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
+            default: wpart = lf_group_id_channel<8>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
+        }
+        const float wsum = lf_block_sum_f(wpart, red);
+        const float sg = c_tab.sigma[c];
+        if (tid == 0) g.wbuf[(size_t) r * g.C + c] = wsum > 0.0f ? (sg > 0.0f ? 1.0f / (c_tab.sigma2[c] * wsum) : 1.0f / wsum) : 1.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Weighted aggregation (core:496-526 / :1297-1327), deterministic and in the reference's order. One CTA per
 // 16x16 pixel tile of one SAI: every thread owns one pixel (all channels) and adds, in (reference patch, n) order —
 // the order the reference's serial loops produce for any given pixel — the contributions of every staged patch

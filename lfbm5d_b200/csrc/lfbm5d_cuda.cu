@@ -452,7 +452,10 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
                                           : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kfn<<<R, 256, smem, ctx->stream>>>(ga);
+    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8)
+        k_groups_id16<<<R, 256, 0, ctx->stream>>>(ga);      // register-resident path (no 2-D transform to stage)
+    else
+        kfn<<<R, 256, smem, ctx->stream>>>(ga);
     ctx->stats.kernel_launches++;
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     {   // ordered aggregation of the staged patches
