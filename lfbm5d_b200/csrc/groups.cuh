@@ -552,19 +552,26 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
 // transform along the similar patches, the hard threshold and both inverses. No shared-memory staging, all gathers of a
 // thread in flight at once, one block reduction per channel for the weight. Same arithmetic as k_groups (bit-identical).
 // ------------------------------------------------------------------------------------------------------------
-template <int NS>
-__device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const unsigned *sofs, const unsigned char *szero, const GroupShape &sh,
-                                                     bool use_sadct, unsigned tofs, int c, int lg, float *zdst, int k2)
+template <int NS, int CC>
+__device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const unsigned *sofs, const GroupShape &sh, bool use_sadct,
+                                                     unsigned tofs, int c, int lg, float *zdst)
 {
-    constexpr int A = 9;
+    constexpr int A = 9, k2 = 256;
+    const int C = CC ? CC : g.C;
     float x[NS][A];
+    {   // masked / out-of-row patches point at the zero block behind the window buffers: no predicates in the gather
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(sofs);
 #pragma unroll
-    for (int n = 0; n < NS; ++n)
+        for (int q4 = 0; q4 < (NS * A + 3) / 4; ++q4) {
+            const uint4 o = s4[q4];
+            const unsigned ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int st = 0; st < A; ++st) {
-            const int pa = n * A + st;
-            x[n][st] = szero[pa] ? 0.f : __ldg(g.nsym + sofs[pa] + tofs);
+            for (int e = 0; e < 4; ++e) {
+                const int pa = q4 * 4 + e;
+                if (pa < NS * A) x[pa / A][pa % A] = __ldg(g.nsym + (ov[e] + tofs));
+            }
         }
+    }
     if (g.tau_4D != 4) {
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
@@ -616,19 +623,20 @@ __device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const u
             } else lf_dct4_inv<3>(x[n]);
         }
     }
+    float *zc = zdst + c * k2;
 #pragma unroll
     for (int n = 0; n < NS; ++n)
 #pragma unroll
-        for (int st = 0; st < A; ++st) zdst[((n * A + st) * g.C + c) * k2] = x[n][st];
+        for (int st = 0; st < A; ++st) zc[(n * A + st) * C * k2] = x[n][st];
     return wpart;
 }
 
+template <int CC>
 __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
 {
     __shared__ GroupShape sh;
     __shared__ float red[8];
-    __shared__ unsigned sofs[LF_MAXN * LF_MAXA];
-    __shared__ unsigned char szero[LF_MAXN * LF_MAXA];
+    __shared__ __align__(16) unsigned sofs[8 * 9];
     constexpr int A = 9, k = 16, k2 = 256;
     const int tid = threadIdx.x;
     const int r = blockIdx.x;
@@ -643,8 +651,8 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
         const int n = t / A, st = t - n * A;
         const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
         const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
-        sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv;
-        szero[t] = (!g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k) ? 1 : 0;
+        const bool zero = !g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k;
+        sofs[t] = zero ? (unsigned) A * (unsigned) g.C * plane : (unsigned) st * (unsigned) g.C * plane + pv;
         g.spos[((size_t) r * g.N + n) * A + st] = pv;
     }
     if (tid == 0) {
@@ -681,10 +689,10 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
         const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
         float wpart;
         switch (nSx) {
-            case 1:  wpart = lf_group_id_channel<1>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
-            case 2:  wpart = lf_group_id_channel<2>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
-            case 4:  wpart = lf_group_id_channel<4>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
-            default: wpart = lf_group_id_channel<8>(g, sofs, szero, sh, use_sadct, tofs, c, lg, zdst, k2); break;
+            case 1:  wpart = lf_group_id_channel<1, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
+            case 2:  wpart = lf_group_id_channel<2, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
+            case 4:  wpart = lf_group_id_channel<4, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
+            default: wpart = lf_group_id_channel<8, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
         }
         const float wsum = lf_block_sum_f(wpart, red);
         const float sg = c_tab.sigma[c];

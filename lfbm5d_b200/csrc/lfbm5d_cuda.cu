@@ -287,7 +287,7 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
 {
     const size_t plane = (size_t) pc.wb * pc.hb, R = pc.rows.size() * pc.cols.size();
     const size_t Ns = 2 * pc.nSim + 1, nself = (pc.nSim + 1) * Ns, Nd = 2 * pc.nDisp + 1;
-    if (ctx->nsym.ensure(pc.A * pc.C * plane * 4) || ctx->numsym.ensure(pc.A * pc.C * plane * 4) ||
+    if (ctx->nsym.ensure((pc.A + 1) * pc.C * plane * 4) || ctx->numsym.ensure(pc.A * pc.C * plane * 4) ||
         ctx->densym.ensure(pc.A * pc.C * plane * 4) || ctx->est0.ensure(pc.A * plane * 4)) return 1;
     if (pc.step == 2 && ctx->bsym.ensure(pc.A * pc.C * plane * 4)) return 1;
     if (pc.N > 1 && (ctx->s_at.ensure(nself * R * 4) || ctx->s_mir.ensure(nself * R * 4))) return 1;
@@ -452,8 +452,13 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
                                           : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8)
-        k_groups_id16<<<R, 256, 0, ctx->stream>>>(ga);      // register-resident path (no 2-D transform to stage)
+    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8) {
+        // register-resident path (no 2-D transform to stage); patches that contribute zeros read the zero block behind nsym
+        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga);
+        else if (pc.C == 1) k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga);
+        else k_groups_id16<0><<<R, 256, 0, ctx->stream>>>(ga);
+    }
     else
         kfn<<<R, 256, smem, ctx->stream>>>(ga);
     ctx->stats.kernel_launches++;
