@@ -718,20 +718,26 @@ struct AggArgs {
     LfWindow win;
 };
 #define AGG_CAP 768
-struct AggEntry { unsigned yx, zidx; float w[3]; };
 
+// K, CC: compile-time patch size / channel count (0 = take them from the arguments)
+template <int K, int CC>
 __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
 {
-    __shared__ AggEntry list[AGG_CAP];
+    __shared__ uint2 lpos[AGG_CAP];                  // (y << 16 | x) of the patch, index of its first channel in zbuf (units of k^2)
+    __shared__ float4 lw[AGG_CAP];                   // per-channel weights of its group
+    __shared__ unsigned short wlist[8][AGG_CAP];     // per warp: the listed patches that touch the warp's 8x4 pixels, in list order
     __shared__ float skaiser[LF_MAXK * LF_MAXK];
     __shared__ int wcount[8];
     __shared__ int s_total;
     const int st = blockIdx.z;
     if (!g.win.mask[st] || g.win.proc[st]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = g.k, k2 = k * k, A = g.A, C = g.C, N = g.N;
+    const int k = K ? K : g.k, k2 = k * k, A = g.A, C = CC ? CC : g.C, N = g.N;
     const int y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
-    const int y = y0 + (tid >> 4), x = x0 + (tid & 15);
+    // a warp owns an 8 (x) by 4 (y) block of the tile: the squarer the footprint, the fewer patches touch it and the more
+    // of its lanes each of them covers
+    const int wy0 = y0 + (warp >> 1) * 4, wx0 = x0 + (warp & 1) * 8;
+    const int y = wy0 + (lane >> 3), x = wx0 + (lane & 7);
     const bool inimg = y < g.h && x < g.w;
     const size_t plane = (size_t) g.w * g.h;
     for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
@@ -744,60 +750,81 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
         for (int c = 0; c < C; ++c) { num[c] = g.numsym[pix + c * plane]; den[c] = g.densym[pix + c * plane]; }
     if (tid == 0) s_total = 0;
     __syncthreads();
-
+    // pixels outside the image never match: their coordinates are moved out of every patch's reach
+    const int ty = inimg ? y : -0x4000, tx = inimg ? x : -0x4000;
+    const float *__restrict__ zb = g.zbuf;
 
     // add the listed patches in list order; the loads of eight consecutive entries are issued before any of them is added
-    // (memory-level parallelism: only ~1/4 of the lanes are covered by a given patch)
-    const int tyx = (y - y0) * 16 + (x - x0);      // unused placeholder to keep per-thread constants together
-    (void) tyx;
+    // (memory-level parallelism: about half of the lanes are covered by a given patch)
     auto flush = [&]() {
-        const int cnt = s_total;
+        const int total = s_total;
+        int cnt = 0;
+        for (int i0 = 0; i0 < total; i0 += 32) {
+            const int i = i0 + lane;
+            bool ov = false;
+            if (i < total) {
+                const unsigned yx = lpos[i].x;
+                const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);
+                ov = py < wy0 + 4 && py + k > wy0 && px < wx0 + 8 && px + k > wx0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ov);
+            if (ov) wlist[warp][cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short) i;
+            cnt += __popc(m);
+        }
+        // pad to a multiple of the batch with an entry that covers nothing (index AGG_CAP - 1 is reserved for it)
         constexpr int U = 8;
-        for (int i0 = 0; i0 < cnt; i0 += U) {
+        const int cpad = (cnt + U - 1) / U * U;
+        if (lane < cpad - cnt) wlist[warp][cnt + lane] = (unsigned short) (AGG_CAP - 1);
+        __syncwarp();
+        const unsigned short *wl = wlist[warp];
+        for (int i0 = 0; i0 < cpad; i0 += U) {
             float z[U][3], kv[U];
-            unsigned on = 0;
+            int idx[U];
+            bool on[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u;
-                if (i < cnt) {
-                    const unsigned yx = list[i].yx;
-                    const int dy = y - (int) (yx >> 16), dx = x - (int) (yx & 0xffffu);
-                    if ((unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k && inimg) {
-                        on |= 1u << u;
-                        const int pq = dy * k + dx;
-                        kv[u] = skaiser[pq];
-                        const float *zp = g.zbuf + (size_t) list[i].zidx * k2 + pq;
+                const int i = idx[u] = wl[i0 + u];
+                const uint2 e = lpos[i];
+                const int dy = ty - (int) (e.x >> 16), dx = tx - (int) (e.x & 0xffffu);
+                on[u] = (unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k;
+                const int pq = dy * k + dx;
+                if (on[u]) {
+                    kv[u] = skaiser[pq];
+                    const float *zp = zb + ((size_t) e.y * (unsigned) k2 + (unsigned) pq);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
-                    }
+                    for (int c = 0; c < 3; ++c) z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (on & (1u << u)) {
+            for (int u = 0; u < U; ++u) {
+                const float4 wv = lw[idx[u]];
+                if (on[u]) {
+                    const float wc[3] = {wv.x, wv.y, wv.z};
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         if (c < C) {
-                            const float kw = kv[u] * list[i0 + u].w[c];
+                            const float kw = kv[u] * wc[c];
                             num[c] += kw * z[u][c];
                             den[c] += kw;
                         }
                 }
+            }
         }
         __syncthreads();
         if (tid == 0) s_total = 0;
         __syncthreads();
     };
 
+    if (tid == 0) lpos[AGG_CAP - 1] = make_uint2(0x7fff7fffu, 0u);     // the padding entry: far away from every pixel
     if (a_hi >= a_lo && nbn > 0) {
         for (int a = a_lo; a <= a_hi; ++a) {
             for (int base = 0; base < nbn; base += 256) {
-                if (s_total + 256 > AGG_CAP) flush();
+                if (s_total + 256 > AGG_CAP - 1) flush();
                 // ---- candidates (a, b, n) in the reference's order; keep those whose patch covers the tile ----
                 const int bn = base + tid;
                 bool hit = false;
-                AggEntry e;
-                e.yx = 0; e.zidx = 0; e.w[0] = e.w[1] = e.w[2] = 0.f;
+                uint2 e = make_uint2(0u, 0u);
+                float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (bn < nbn) {
                     const int n = bn & (N - 1), b = b_lo + (bn >> g.log2N);
                     const int r = a * g.nc + b;
@@ -806,9 +833,10 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
                         const int py = (int) (pos / (unsigned) g.w), px = (int) (pos - (unsigned) py * (unsigned) g.w);
                         if (py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0) {
                             hit = true;
-                            e.yx = ((unsigned) py << 16) | (unsigned) px;
-                            e.zidx = (unsigned) ((((size_t) r * N + n) * A + st) * C);
-                            for (int c = 0; c < C; ++c) e.w[c] = g.wbuf[(size_t) r * C + c];
+                            e.x = ((unsigned) py << 16) | (unsigned) px;
+                            e.y = (unsigned) ((((size_t) r * N + n) * A + st) * C);
+                            ew.x = g.wbuf[(size_t) r * C];
+                            if (C > 1) { ew.y = g.wbuf[(size_t) r * C + 1]; ew.z = g.wbuf[(size_t) r * C + 2]; }
                         }
                     }
                 }
@@ -817,7 +845,7 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
                 __syncthreads();
                 int off = s_total, tot = 0;
                 for (int wv = 0; wv < 8; ++wv) { if (wv < warp) off += wcount[wv]; tot += wcount[wv]; }
-                if (hit) list[off + __popc(m & ((1u << lane) - 1u))] = e;
+                if (hit) { const int o = off + __popc(m & ((1u << lane) - 1u)); lpos[o] = e; lw[o] = ew; }
                 __syncthreads();
                 if (tid == 0) s_total += tot;
                 __syncthreads();

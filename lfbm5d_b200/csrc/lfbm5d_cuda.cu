@@ -474,7 +474,12 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
         aa.win = win;
         dim3 grid((pc.wb + 15) / 16, (pc.hb + 15) / 16, pc.A);
-        LAUNCH(ctx, k_aggregate, grid, 256, 0, aa);
+        void (*kagg)(AggArgs) = k_aggregate<0, 0>;
+        if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
+        else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
+        else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
+        else if (pc.C == 1 && pc.k == 8) kagg = k_aggregate<8, 1>;
+        LAUNCH(ctx, kagg, grid, 256, 0, aa);
     }
     CK(cudaGetLastError());
     ctx->stats.window_passes++;
