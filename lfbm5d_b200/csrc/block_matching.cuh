@@ -54,38 +54,6 @@ template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 // staged once per CTA with cp.async into two 128-row shared-memory rings (row stride 64 floats: the skewed reads
 // are bank-conflict free) and reused by all planes of the group; squared differences are formed on the fly.
 // ---- packed FP32x2 arithmetic (FADD2 / FMUL2 on sm_100): two planes per lane, IEEE per half ----
-__device__ __forceinline__ unsigned long long lf_pk(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void lf_upk(unsigned long long v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long lf_add2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long lf_sub2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// Exact packed product. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (observed, CUDA 12.9) even with
-// -fmad=false — also when the product is written as fma(a, b, -0) with a literal -0 — which would change the rounding of
-// the recurrence. With the -0 addend supplied at run time (SatGeom::negzero2) ptxas cannot fold it: fma(a, b, -0) is the
-// exact product (round(a*b + -0) = round(a*b), +0 for a zero product) and stays separate from the following add.
-__device__ __forceinline__ unsigned long long lf_mul2(unsigned long long a, unsigned long long b, unsigned long long negzero)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
-    return r;
-}
 
 // Summed-area planes, v3. As v2, with TWO planes per lane (column offsets ox and ox+1 of the same group): the img1
 // operand is shared, the img2 operands are adjacent ring entries, and all floating-point work of the step runs as packed

@@ -53,6 +53,46 @@ __device__ __forceinline__ void lf_cp_async_wait_all()
 }
 
 
+// ---- packed FP32x2 arithmetic (two independent IEEE operations per instruction; sm_100 FADD2 / FFMA2) ----
+__device__ __forceinline__ unsigned long long lf_pk(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void lf_upk(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long lf_add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long lf_sub2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Exact packed product. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (observed, CUDA 12.9) even with
+// -fmad=false — also when the product is written as fma(a, b, -0) with a literal -0 — which would change the rounding of
+// the recurrence. With the -0 addend supplied at run time (SatGeom::negzero2) ptxas cannot fold it: fma(a, b, -0) is the
+// exact product (round(a*b + -0) = round(a*b), +0 for a zero product) and stays separate from the following add.
+__device__ __forceinline__ unsigned long long lf_mul2(unsigned long long a, unsigned long long b, unsigned long long negzero)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(negzero));
+    return r;
+}
+__device__ __forceinline__ unsigned long long lf_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // release/acquire flag accesses at GPU scope (producer/consumer hand-off between CTAs)
 __device__ __forceinline__ void lf_st_release(int *p, int v)
 {

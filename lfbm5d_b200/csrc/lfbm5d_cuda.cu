@@ -6,6 +6,7 @@
 #include "elementwise.cuh"
 #include "block_matching.cuh"
 #include "groups.cuh"
+#include "groups_wiener8.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -289,7 +290,7 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
     const size_t Ns = 2 * pc.nSim + 1, nself = (pc.nSim + 1) * Ns, Nd = 2 * pc.nDisp + 1;
     if (ctx->nsym.ensure((pc.A + 1) * pc.C * plane * 4) || ctx->numsym.ensure(pc.A * pc.C * plane * 4) ||
         ctx->densym.ensure(pc.A * pc.C * plane * 4) || ctx->est0.ensure(pc.A * plane * 4)) return 1;
-    if (pc.step == 2 && ctx->bsym.ensure(pc.A * pc.C * plane * 4)) return 1;
+    if (pc.step == 2 && ctx->bsym.ensure((pc.A + 1) * pc.C * plane * 4)) return 1;
     if (pc.N > 1 && (ctx->s_at.ensure(nself * R * 4) || ctx->s_mir.ensure(nself * R * 4))) return 1;
     // stereo sums in the skewed layout of k_sat2: [plane][strip][SR][32]
     const size_t st_cols = pc.wb - 2 * pc.nDisp - pc.k + 1, st_rows = pc.hb - 2 * pc.nDisp - pc.k + 1;
@@ -458,6 +459,15 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga);
         else if (pc.C == 1) k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga);
         else k_groups_id16<0><<<R, 256, 0, ctx->stream>>>(ga);
+    }
+    else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR) {
+        // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
+        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : (pc.C == 1 ? k_groups_w8<1> : k_groups_w8<0>);
+        const size_t smem8 = (size_t) 16 * 9 * W8_PS * 8;
+        CK(cudaFuncSetAttribute((const void *) k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8));
+        k8<<<R, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
     }
     else
         kfn<<<R, 256, smem, ctx->stream>>>(ga);
