@@ -12,6 +12,8 @@
 #define W8_RS 10      // packed values per patch row: 8 + 2 (row reads of eight lanes hit distinct banks)
 #define W8_PS 88      // packed values per patch (8 rows * 10 + 8; = 16 banks mod 32: two patches per half warp are disjoint)
 #define W8_NT 288
+#define W8_ZRS 10     // filtered signal: packed (row p, row p+4) values per row pair, 4 row pairs per patch
+#define W8_ZPS 40     // packed values per patch of the filtered signal (= 16 banks mod 32 as well)
 
 typedef unsigned long long lf_f2;
 
@@ -237,9 +239,9 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
     w8_pos((tid + W8_NT) & 63, p1, q1);
     const int st0 = tid >> 6, st1 = (tid + W8_NT) >> 6;
     const int pos0 = st0 * W8_PS + p0 * W8_RS + q0, pos1 = st1 * W8_PS + p1 * W8_RS + q1;
-    // same items in the layout of the filtered signal: float index ((p & 3) * 8 + q) * 2 + (p >> 2) inside the patch
-    const int zo0 = st0 * (2 * W8_PS) + ((p0 & 3) * 8 + q0) * 2 + (p0 >> 2);
-    const int zo1 = st1 * (2 * W8_PS) + ((p1 & 3) * 8 + q1) * 2 + (p1 >> 2);
+    // same items in the layout of the filtered signal: float index ((p & 3) * W8_ZRS + q) * 2 + (p >> 2) inside the patch
+    const int zo0 = st0 * (2 * W8_ZPS) + ((p0 & 3) * W8_ZRS + q0) * 2 + (p0 >> 2);
+    const int zo1 = st1 * (2 * W8_ZPS) + ((p1 & 3) * W8_ZRS + q1) * 2 + (p1 >> 2);
     const int pr = tid & 3;                                    // inverse 2-D: rows (pr, pr + 4) / columns (2 pr, 2 pr + 1)
     lf_f2 cni_row[8];                                          // inverse pre-scaling of rows pr (low) and pr + 4 (high)
 #pragma unroll
@@ -322,8 +324,8 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
             if (n < nSx) {
                 float a, b;
                 lf_upk(out[n], a, b);
-                Pf[n * 9 * (2 * W8_PS) + zo0] = a;
-                Pf[n * 9 * (2 * W8_PS) + zo1] = b;
+                Pf[n * 9 * (2 * W8_ZPS) + zo0] = a;
+                Pf[n * 9 * (2 * W8_ZPS) + zo1] = b;
             }
         if (tid == 0) {
             float wsum = 0.f;
@@ -334,14 +336,18 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
         __syncthreads();
         // ---- inverse angular transform (core:1231-1250), rows (p, p+4) of a patch packed ----
         if (g.tau_4D != 4) {
-            for (int it = tid; it < nSx * 32; it += W8_NT) {
-                lf_f2 *b = P + (it >> 5) * 9 * W8_PS + lane;
-                lf_f2 v[9];
+            // a half warp = one row pair of two consecutive n (their patches are 16 banks apart)
+            for (int it = tid; it < ((nSx + 1) & ~1) * 32; it += W8_NT) {
+                const int n = 2 * (it >> 6) + ((lane >> 3) & 1), prd = ((it >> 5) & 1) * 2 + (lane >> 4);
+                if (n < nSx) {
+                    lf_f2 *b = P + n * 9 * W8_ZPS + prd * W8_ZRS + (lane & 7);
+                    lf_f2 v[9];
 #pragma unroll
-                for (int st = 0; st < 9; ++st) v[st] = b[st * W8_PS];
-                if (use_sadct) w8_sadct(v, sh, false); else w8_dct4_inv(v, nz2);
+                    for (int st = 0; st < 9; ++st) v[st] = b[st * W8_ZPS];
+                    if (use_sadct) w8_sadct(v, sh, false); else w8_dct4_inv(v, nz2);
 #pragma unroll
-                for (int st = 0; st < 9; ++st) b[st * W8_PS] = v[st];
+                    for (int st = 0; st < 9; ++st) b[st * W8_ZPS] = v[st];
+                }
             }
             __syncthreads();
         }
@@ -350,10 +356,10 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
             const int it = base + tid;
             const bool act = it < npatch * 4;
             const int pa = it >> 2;
-            lf_f2 *pb = P + pa * W8_PS;
+            lf_f2 *pb = P + pa * W8_ZPS;
             if (act) {
                 lf_f2 v[8], o[8];
-                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(pb + pr * 8);
+                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(pb + pr * W8_ZRS);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const ulonglong2 t = row[j];
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
                 lf_f2 v[8], o[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {      // rows j (low halves) and j + 4 (high halves) at columns 2 pr, 2 pr + 1
-                    const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(pb + j * 8 + 2 * pr);
+                    const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(pb + j * W8_ZRS + 2 * pr);
                     float a0, a4, b0, b4;
                     lf_upk(t.x, a0, a4);
                     lf_upk(t.y, b0, b4);
