@@ -17,10 +17,14 @@ struct GroupArgs {
     // staging for the ordered aggregation kernel (k_aggregate): filtered patches, weights, positions, flags
     float *zbuf;                                  // [R][N][A][C][k2]
     float *wbuf;                                  // [R][C]
-    unsigned *spos;                               // [R][N][A] flat position of every gathered patch
-    unsigned char *gflag;                         // [R][A] 1 = this SAI's patches of the group are aggregated
+    const unsigned short *gmask;                  // [R] bit st = SAI st takes part in the group's angular shape (k_group_masks)
+    const struct GroupShape *shape_lut;           // [2^A] SA-DCT index tables per shape (host-built, core:300-330)
+    unsigned *ent;                                // [A][R*N] (y << 16 | x) of every patch that is aggregated, else LF_NOENT
+    int R;
     LfWindow win;
 };
+
+#define LF_NOENT 0xffffffffu
 
 struct GroupShape {
     unsigned mask[LF_MAXA], idx[LF_MAXA], idx_col[LF_MAXA], mask_dct[LF_MAXA];
@@ -388,6 +392,55 @@ __device__ __forceinline__ void lf_t2d(float *B, int npatch, const GroupArgs &g,
     }
 }
 
+// Per-group set-up shared by the group kernels (core:277-299, :486-503): SA-DCT shape of the group, source offset of every
+// gathered patch (ZB: patches that read as zeros point at the zero block behind the window buffers, else szero marks them),
+// and the aggregation entries: (y << 16 | x) of every patch that k_aggregate has to add, LF_NOENT otherwise.
+template <bool ZB>
+__device__ __forceinline__ void lf_group_setup(const GroupArgs &g, int r, int nSx, GroupShape &sh, unsigned *sofs, unsigned char *szero)
+{
+    __shared__ unsigned s_yx[LF_MAXN * LF_MAXA];
+    const int A = g.A, w = g.w, k = g.k;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned plane = (unsigned) g.w * (unsigned) g.h;
+    if (tid >= nt - 32) {        // the last warp copies the group's SA-DCT tables, beside the offset loop of the first warps
+        const unsigned *src = reinterpret_cast<const unsigned *>(g.shape_lut + g.gmask[r]);
+        unsigned *dst = reinterpret_cast<unsigned *>(&sh);
+        for (int i = tid - (nt - 32); i < (int) (sizeof(GroupShape) / 4); i += 32) dst[i] = src[i];
+    }
+    for (int t = tid; t < nSx * A; t += nt) {
+        const int n = t / A, st = t - n * A;
+        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
+        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
+        const unsigned py = pv / (unsigned) w, px = pv - py * (unsigned) w;
+        const bool zero = !g.win.mask[st] || (int) px >= w - k;       // empty SAI, or column w-k (core:1697)
+        if (ZB) sofs[t] = zero ? (unsigned) A * (unsigned) g.C * plane : (unsigned) st * (unsigned) g.C * plane + pv;
+        else { sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv; szero[t] = zero ? 1 : 0; }
+        s_yx[t] = (py << 16) | px;
+    }
+    __syncthreads();
+    for (int t = tid; t < g.N * A; t += nt) {
+        const int n = t / A, st = t - n * A;
+        // core:486, :503: which SAIs receive this group's patches
+        const bool on = n < nSx && !g.win.proc[st] && !(g.tau_4D == 6 && st != g.pst && !sh.mask[st]);
+        g.ent[(size_t) st * g.R * g.N + (size_t) r * g.N + n] = on ? s_yx[t] : LF_NOENT;
+    }
+}
+
+// bit st of gmask[r]: SAI st belongs to the angular shape of reference patch r (core:300-312)
+__global__ void k_group_masks(const int *__restrict__ rows, const int *__restrict__ cols, int nc, int R, int w, unsigned plane, int A, int pst,
+                              LfWindow win, const unsigned char *__restrict__ shape, unsigned short *__restrict__ gmask)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int k_r = rows[r / nc] * w + cols[r % nc];
+    unsigned m = 0;
+    for (int st = 0; st < A; ++st) {
+        const unsigned b = (st == pst) ? 1u : (win.mask[st] ? (unsigned) shape[(size_t) st * plane + k_r] : 0u);
+        m |= (b ? 1u : 0u) << st;
+    }
+    gmask[r] = (unsigned short) m;
+}
+
 template <int STEP, int ASW>
 __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
 {
@@ -401,7 +454,6 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     const int r = blockIdx.x;
     const int k = g.k, k2 = k * k, w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
-    const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
     const int nSx = (int) g.bm_count[r];
     const int lg = 31 - __clz(nSx);
     const int PS = g.PS, RS = g.RS;
@@ -413,44 +465,8 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     const int p = pq >> g.log2k, q = pq & (k - 1);
     const int poff = p * RS + q;
     const int npatch = nSx * A;
-
-    for (int t = tid; t < npatch; t += 256) {
-        const int n = t / A, st = t - n * A;
-        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
-        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
-        sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv;
-        szero[t] = (!g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k) ? 1 : 0;
-        g.spos[((size_t) r * g.N + n) * A + st] = pv;
-    }
-    if (tid == 0) {
-        unsigned size = 0;
-        for (int st = 0; st < A; ++st) {
-            const unsigned m = (st == g.pst) ? 1u : (g.win.mask[st] ? (unsigned) g.shape[(size_t) st * plane + k_r] : 0u);
-            sh.mask[st] = m; size += m;
-            sh.idx[st] = 0; sh.idx_col[st] = 0; sh.mask_dct[st] = 0;
-        }
-        sh.use_sadct = (g.tau_4D == 6) && (size != (unsigned) A);
-        if (g.tau_4D == 6) {
-            unsigned mask_col[LF_MAXA];
-            for (int st = 0; st < A; ++st) mask_col[st] = 0;
-            for (int s = 0; s < ASW; ++s) {
-                unsigned rr = 0;
-                for (int t = 0; t < ASW; ++t) if (sh.mask[s * ASW + t]) sh.idx[s * ASW + rr++] = t;
-                sh.row_size[s] = rr;
-                for (unsigned t = 0; t < rr; ++t) mask_col[s * ASW + t] = 1;
-            }
-            for (int t = 0; t < ASW; ++t) {
-                unsigned rr = 0;
-                for (int s = 0; s < ASW; ++s) if (mask_col[s * ASW + t]) sh.idx_col[(rr++) * ASW + t] = s;
-                sh.col_size[t] = rr;
-                for (unsigned s = 0; s < rr; ++s) sh.mask_dct[s * ASW + t] = 1;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < A)      // core:486, :503: which SAIs receive this group's patches
-        g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
-    const bool use_sadct = sh.use_sadct != 0;
+    lf_group_setup<false>(g, r, nSx, sh, sofs, szero);
+    const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
     float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
 
     for (int c = 0; c < g.C; ++c) {
@@ -642,48 +658,11 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
     const int r = blockIdx.x;
     const int w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
-    const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
     const int nSx = (int) g.bm_count[r];
     const int lg = 31 - __clz(nSx);
     const int pq = tid, p = pq >> 4, q = pq & 15;
-    const int npatch = nSx * A;
-    for (int t = tid; t < npatch; t += 256) {
-        const int n = t / A, st = t - n * A;
-        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
-        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
-        const bool zero = !g.win.mask[st] || (int) (pv % (unsigned) w) >= w - k;
-        sofs[t] = zero ? (unsigned) A * (unsigned) g.C * plane : (unsigned) st * (unsigned) g.C * plane + pv;
-        g.spos[((size_t) r * g.N + n) * A + st] = pv;
-    }
-    if (tid == 0) {
-        unsigned size = 0;
-        for (int st = 0; st < A; ++st) {
-            const unsigned m = (st == g.pst) ? 1u : (g.win.mask[st] ? (unsigned) g.shape[(size_t) st * plane + k_r] : 0u);
-            sh.mask[st] = m; size += m;
-            sh.idx[st] = 0; sh.idx_col[st] = 0; sh.mask_dct[st] = 0;
-        }
-        sh.use_sadct = (g.tau_4D == 6) && (size != (unsigned) A);
-        if (g.tau_4D == 6) {
-            unsigned mask_col[LF_MAXA];
-            for (int st = 0; st < A; ++st) mask_col[st] = 0;
-            for (int s = 0; s < 3; ++s) {
-                unsigned rr = 0;
-                for (int t = 0; t < 3; ++t) if (sh.mask[s * 3 + t]) sh.idx[s * 3 + rr++] = t;
-                sh.row_size[s] = rr;
-                for (unsigned t = 0; t < rr; ++t) mask_col[s * 3 + t] = 1;
-            }
-            for (int t = 0; t < 3; ++t) {
-                unsigned rr = 0;
-                for (int s = 0; s < 3; ++s) if (mask_col[s * 3 + t]) sh.idx_col[(rr++) * 3 + t] = s;
-                sh.col_size[t] = rr;
-                for (unsigned s = 0; s < rr; ++s) sh.mask_dct[s * 3 + t] = 1;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < A)
-        g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
-    const bool use_sadct = sh.use_sadct != 0;
+    lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr);
+    const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
     float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
     for (int c = 0; c < g.C; ++c) {
         const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
@@ -709,9 +688,8 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
 // ------------------------------------------------------------------------------------------------------------
 struct AggArgs {
     int C, A, k, N, log2N, w, h, nc;
-    const unsigned *bm_count;      // [R]
-    const unsigned *spos;          // [R][N][A]
-    const unsigned char *gflag;    // [R][A]
+    int R;
+    const unsigned *ent;           // [A][R*N] (y << 16 | x) of the patches to add, LF_NOENT for the others (lf_group_setup)
     const float *zbuf, *wbuf;
     float *numsym, *densym;
     const int *arange, *brange;    // per tile row / tile column: first and last candidate reference row / column index
@@ -727,8 +705,7 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
     __shared__ float4 lw[AGG_CAP];                   // per-channel weights of its group
     __shared__ unsigned short wlist[8][AGG_CAP];     // per warp: the listed patches that touch the warp's 8x4 pixels, in list order
     __shared__ float skaiser[LF_MAXK * LF_MAXK];
-    __shared__ int wcount[8];
-    __shared__ int s_total;
+    __shared__ int wcount[2][8];
     const int st = blockIdx.z;
     if (!g.win.mask[st] || g.win.proc[st]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -748,16 +725,14 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
     const size_t pix = ((size_t) st * C) * plane + (size_t) y * g.w + x;
     if (inimg)
         for (int c = 0; c < C; ++c) { num[c] = g.numsym[pix + c * plane]; den[c] = g.densym[pix + c * plane]; }
-    if (tid == 0) s_total = 0;
-    __syncthreads();
     // pixels outside the image never match: their coordinates are moved out of every patch's reach
     const int ty = inimg ? y : -0x4000, tx = inimg ? x : -0x4000;
     const float *__restrict__ zb = g.zbuf;
 
     // add the listed patches in list order; the loads of eight consecutive entries are issued before any of them is added
     // (memory-level parallelism: about half of the lanes are covered by a given patch)
-    auto flush = [&]() {
-        const int total = s_total;
+    auto flush = [&](const int total) {
+        __syncthreads();                 // the list is complete
         int cnt = 0;
         for (int i0 = 0; i0 < total; i0 += 32) {
             const int i = i0 + lane;
@@ -810,48 +785,46 @@ __global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0) s_total = 0;
-        __syncthreads();
+        __syncthreads();                 // the list can be overwritten
     };
 
     if (tid == 0) lpos[AGG_CAP - 1] = make_uint2(0x7fff7fffu, 0u);     // the padding entry: far away from every pixel
     if (a_hi >= a_lo && nbn > 0) {
+        const unsigned *ent = g.ent + (size_t) st * g.R * N;
+        int total = 0, buf = 0;            // entries listed so far (identical in every thread)
         for (int a = a_lo; a <= a_hi; ++a) {
+            const unsigned *erow = ent + ((size_t) a * g.nc + b_lo) * N;      // candidates (b, n) of this reference row are contiguous
             for (int base = 0; base < nbn; base += 256) {
-                if (s_total + 256 > AGG_CAP - 1) flush();
+                if (total + 256 > AGG_CAP - 1) { flush(total); total = 0; }
                 // ---- candidates (a, b, n) in the reference's order; keep those whose patch covers the tile ----
                 const int bn = base + tid;
                 bool hit = false;
-                uint2 e = make_uint2(0u, 0u);
-                float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned yx = 0;
                 if (bn < nbn) {
-                    const int n = bn & (N - 1), b = b_lo + (bn >> g.log2N);
-                    const int r = a * g.nc + b;
-                    if (n < (int) g.bm_count[r] && g.gflag[(size_t) r * A + st]) {
-                        const unsigned pos = g.spos[((size_t) r * N + n) * A + st];
-                        const int py = (int) (pos / (unsigned) g.w), px = (int) (pos - (unsigned) py * (unsigned) g.w);
-                        if (py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0) {
-                            hit = true;
-                            e.x = ((unsigned) py << 16) | (unsigned) px;
-                            e.y = (unsigned) ((((size_t) r * N + n) * A + st) * C);
-                            ew.x = g.wbuf[(size_t) r * C];
-                            if (C > 1) { ew.y = g.wbuf[(size_t) r * C + 1]; ew.z = g.wbuf[(size_t) r * C + 2]; }
-                        }
-                    }
+                    yx = __ldg(erow + bn);
+                    const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);       // LF_NOENT: far outside
+                    hit = py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) wcount[warp] = __popc(m);
+                if (lane == 0) wcount[buf][warp] = __popc(m);
                 __syncthreads();
-                int off = s_total, tot = 0;
-                for (int wv = 0; wv < 8; ++wv) { if (wv < warp) off += wcount[wv]; tot += wcount[wv]; }
-                if (hit) { const int o = off + __popc(m & ((1u << lane) - 1u)); lpos[o] = e; lw[o] = ew; }
-                __syncthreads();
-                if (tid == 0) s_total += tot;
-                __syncthreads();
+                int off = total;
+#pragma unroll
+                for (int wv = 0; wv < 8; ++wv) { const int cw = wcount[buf][wv]; if (wv < warp) off += cw; total += cw; }
+                if (hit) {
+                    const int o = off + __popc(m & ((1u << lane) - 1u));
+                    const int rn = (a * g.nc + b_lo) * N + bn;       // r * N + n
+                    const int r = rn >> g.log2N;
+                    lpos[o] = make_uint2(yx, (unsigned) (((size_t) rn * A + st) * C));
+                    float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ew.x = g.wbuf[(size_t) r * C];
+                    if (C > 1) { ew.y = g.wbuf[(size_t) r * C + 1]; ew.z = g.wbuf[(size_t) r * C + 2]; }
+                    lw[o] = ew;
+                }
+                buf ^= 1;
             }
         }
-        flush();
+        flush(total);
     }
     if (inimg)
         for (int c = 0; c < C; ++c) { g.numsym[pix + c * plane] = num[c]; g.densym[pix + c * plane] = den[c]; }

@@ -182,48 +182,11 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
     const int r = blockIdx.x;
     const int w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
-    const int k_r = g.rows[r / g.nc] * w + g.cols[r % g.nc];
     const int nSx = (int) g.bm_count[r];
     const int npatch = nSx * A;
 
-    for (int t = tid; t < npatch; t += W8_NT) {
-        const int n = t / A, st = t - n * A;
-        const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
-        const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
-        // empty SAIs and patches in column w-k (core:1697) read as zeros: they point at the zero block behind the window
-        const bool zero = !g.win.mask[st] || (int) (pv % (unsigned) w) >= w - 8;
-        sofs[t] = zero ? (unsigned) A * (unsigned) C * plane : (unsigned) st * (unsigned) C * plane + pv;
-        g.spos[((size_t) r * g.N + n) * A + st] = pv;
-    }
-    if (tid == 0) {
-        unsigned size = 0;
-        for (int st = 0; st < A; ++st) {
-            const unsigned m = (st == g.pst) ? 1u : (g.win.mask[st] ? (unsigned) g.shape[(size_t) st * plane + k_r] : 0u);
-            sh.mask[st] = m; size += m;
-            sh.idx[st] = 0; sh.idx_col[st] = 0; sh.mask_dct[st] = 0;
-        }
-        sh.use_sadct = (g.tau_4D == 6) && (size != (unsigned) A);
-        if (g.tau_4D == 6) {
-            unsigned mask_col[LF_MAXA];
-            for (int st = 0; st < A; ++st) mask_col[st] = 0;
-            for (int s = 0; s < 3; ++s) {
-                unsigned rr = 0;
-                for (int t = 0; t < 3; ++t) if (sh.mask[s * 3 + t]) sh.idx[s * 3 + rr++] = t;
-                sh.row_size[s] = rr;
-                for (unsigned t = 0; t < rr; ++t) mask_col[s * 3 + t] = 1;
-            }
-            for (int t = 0; t < 3; ++t) {
-                unsigned rr = 0;
-                for (int s = 0; s < 3; ++s) if (mask_col[s * 3 + t]) sh.idx_col[(rr++) * 3 + t] = s;
-                sh.col_size[t] = rr;
-                for (unsigned s = 0; s < rr; ++s) sh.mask_dct[s * 3 + t] = 1;
-            }
-        }
-    }
-    __syncthreads();
-    if (tid < A)
-        g.gflag[(size_t) r * A + tid] = (!g.win.proc[tid] && !(g.tau_4D == 6 && tid != g.pst && !sh.mask[tid])) ? 1 : 0;
-    const bool use_sadct = sh.use_sadct != 0;
+    lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr);
+    const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
 
     // per-thread constants of the phases
     const int q8 = tid & 7;                                    // row index (row pass) / column index (column pass)

@@ -118,7 +118,8 @@ struct lfbm5d_ctx {
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut;
+    unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
     cudaEvent_t ev[5]{};
@@ -304,7 +305,7 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
         ctx->bnd.ensure(nplanes * max_strips * pc.hb * 4) || ctx->progress.ensure((nplanes * max_strips + 4) * 4)) return 1;
     if (ctx->counters.ensure(64 * 8)) return 1;
     if (ctx->zbuf.ensure(R * pc.N * pc.A * pc.C * pc.k * pc.k * 4) || ctx->wbuf.ensure(R * pc.C * 4) ||
-        ctx->spos.ensure(R * pc.N * pc.A * 4) || ctx->gflag.ensure(R * pc.A)) return 1;
+        ctx->spos.ensure(R * pc.N * pc.A * 4)) return 1;
     return 0;
 }
 
@@ -314,6 +315,40 @@ __global__ void k_bm_identity(const int *rows, const int *cols, int nc, int w, i
     if (r >= R) return;
     out_count[r] = 1;
     out_idx[(size_t) r * (N + 1)] = (unsigned) (rows[r / nc] * w + cols[r % nc]);    // core:3448-3460
+}
+
+// SA-DCT index tables for every subset of the angular window (core:300-330: shape_idx, shape_mask_col, shape_idx_col,
+// shape_mask_dct as built by sadct_4d_process, core:1969-2010); the group kernels look them up by the group's mask.
+int ensure_shape_lut(lfbm5d_ctx *ctx, unsigned asw)
+{
+    if (ctx->lut_asw == asw) return 0;
+    const unsigned A = asw * asw, n = 1u << A;
+    std::vector<GroupShape> lut(n);
+    for (unsigned bits = 0; bits < n; bits++) {
+        GroupShape &sh = lut[bits];
+        memset(&sh, 0, sizeof(sh));
+        unsigned size = 0;
+        for (unsigned st = 0; st < A; st++) { sh.mask[st] = (bits >> st) & 1u; size += sh.mask[st]; }
+        sh.use_sadct = size != A;
+        unsigned mask_col[LF_MAXA] = { 0 };
+        for (unsigned s = 0; s < asw; s++) {
+            unsigned rr = 0;
+            for (unsigned t = 0; t < asw; t++) if (sh.mask[s * asw + t]) sh.idx[s * asw + rr++] = t;
+            sh.row_size[s] = rr;
+            for (unsigned t = 0; t < rr; t++) mask_col[s * asw + t] = 1;
+        }
+        for (unsigned t = 0; t < asw; t++) {
+            unsigned rr = 0;
+            for (unsigned s = 0; s < asw; s++) if (mask_col[s * asw + t]) sh.idx_col[(rr++) * asw + t] = s;
+            sh.col_size[t] = rr;
+            for (unsigned s = 0; s < rr; s++) sh.mask_dct[s * asw + t] = 1;
+        }
+    }
+    if (ctx->shape_lut.ensure(n * sizeof(GroupShape))) return 1;
+    CK(cudaMemcpyAsync(ctx->shape_lut.p, lut.data(), n * sizeof(GroupShape), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->lut_asw = asw;
+    return 0;
 }
 
 // One core call on the padded device buffers of the window (nsym/bsym/numsym/densym/est0 already filled).
@@ -431,10 +466,14 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
                (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
                ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane);
     }
+    if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure(R * 2)) return 1;
+    LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) R, (int) pc.wb, (unsigned) plane,
+           (int) pc.A, (int) pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
 
     // ---- groups ----
     GroupArgs ga{};
+    ga.gmask = ctx->gmask.as<unsigned short>(); ga.shape_lut = ctx->shape_lut.as<GroupShape>();
     ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
     ga.pst = pst; ga.nc = nc;
     // row padding removes the shared-memory bank conflicts of the 2-D passes (3 CTAs/SM without it measured slower)
@@ -446,8 +485,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     ga.first = ctx->first.as<unsigned>(); ga.shape = ctx->shape.as<unsigned char>();
     ga.nsym = ctx->nsym.as<float>(); ga.bsym = ctx->bsym.as<float>();
     ga.numsym = ctx->numsym.as<float>(); ga.densym = ctx->densym.as<float>();
-    ga.zbuf = ctx->zbuf.as<float>(); ga.wbuf = ctx->wbuf.as<float>(); ga.spos = ctx->spos.as<unsigned>();
-    ga.gflag = ctx->gflag.as<unsigned char>();
+    ga.zbuf = ctx->zbuf.as<float>(); ga.wbuf = ctx->wbuf.as<float>(); ga.ent = ctx->spos.as<unsigned>(); ga.R = (int) R;
     ga.win = win;
     const size_t smem = (size_t) pc.N * pc.A * ga.PS * 4 * (pc.step == 2 ? 2 : 1);
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
@@ -478,7 +516,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
         while ((1u << aa.log2N) < pc.N) aa.log2N++;
         aa.w = pc.wb; aa.h = pc.hb; aa.nc = nc;
-        aa.bm_count = ctx->bmcount.as<unsigned>(); aa.spos = ctx->spos.as<unsigned>(); aa.gflag = ctx->gflag.as<unsigned char>();
+        aa.R = (int) R; aa.ent = ctx->spos.as<unsigned>();
         aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
         aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
         aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
@@ -793,7 +831,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
