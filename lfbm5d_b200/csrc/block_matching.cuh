@@ -476,23 +476,26 @@ __device__ __forceinline__ float lf_fkey_inv(unsigned key)
     return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
 }
 
+#define LF_SEL_SMALL 128
+
 struct SelGeom {
     int w, nSim, Ns, N, R, nc;
     float threshold;
     const int *rows, *cols;       // reference rows / columns
 };
 
-__global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__restrict__ s_at, const float *__restrict__ s_mir,
-                                                  unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx)
+// One warp selects the matches of reference patch r exactly like the reference (also under exact float ties).
+__device__ __forceinline__ void lf_bm_select_one(const SelGeom &g, const int r, unsigned long long *keys, const float *__restrict__ s_at,
+                                                 const float *__restrict__ s_mir, unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx)
 {
-    extern __shared__ unsigned long long keys[];      // up to Ns*Ns entries, later reused as LfPair[]
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x, r = blockIdx.x;
+    const int lane = threadIdx.x;
     const int k_r = g.rows[r / g.nc] * g.w + g.cols[r % g.nc];
     const int Ns = g.Ns, nSim = g.nSim, total = Ns * Ns;
 
     // candidates in the reference's push order: for dj { di = 0..nSim ; di = -nSim..-1 }
     int cnt = 0;
+    unsigned long long lmin = ~0ull;       // smallest key seen by this lane
     for (int base = 0; base < total; base += 32) {
         const int o = base + lane;
         bool keep = false;
@@ -514,7 +517,9 @@ __global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__rest
         const unsigned m = __ballot_sync(FULL, keep);
         if (keep) {
             const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-            keys[slot] = ((unsigned long long) lf_fkey(val + 0.0f) << 32) | (unsigned) o;
+            const unsigned long long kk = ((unsigned long long) lf_fkey(val + 0.0f) << 32) | (unsigned) o;
+            keys[slot] = kk;
+            lmin = kk < lmin ? kk : lmin;
         }
         cnt += __popc(m);
     }
@@ -528,11 +533,41 @@ __global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__rest
     }
     // the M = min(cnt, nSx+1) smallest keys, ascending; lane t keeps the t-th (t < 32), `extra` the 33rd
     const int M = min(cnt, (int) nSx + 1);
+    // pruning: the M-th smallest of the 32 per-lane minima bounds the M-th smallest key from above; the selection rounds
+    // then run on the few keys below that bound (the full list stays in place for the tie path)
+    __shared__ unsigned long long small[LF_SEL_SMALL];
+    const unsigned long long *sel = keys;
+    int nsel = cnt;
+    if (cnt > LF_SEL_SMALL && M <= 32) {
+        unsigned long long bound = 0, pv = 0;
+        for (int t = 0; t < M; ++t) {
+            unsigned long long best = (t == 0 || lmin > pv) ? lmin : ~0ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+                best = other < best ? other : best;
+            }
+            pv = bound = best;
+        }
+        if (bound != ~0ull) {           // at least M lanes hold a candidate
+            int c2 = 0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int q = base + lane;
+                const unsigned long long kq = q < cnt ? keys[q] : ~0ull;
+                const bool keep = kq <= bound;
+                const unsigned m = __ballot_sync(FULL, keep);
+                const int slot = c2 + __popc(m & ((1u << lane) - 1u));
+                if (keep && slot < LF_SEL_SMALL) small[slot] = kq;
+                c2 += __popc(m);
+            }
+            __syncwarp();
+            if (c2 <= LF_SEL_SMALL) { sel = small; nsel = c2; }
+        }
+    }
     unsigned long long prev = 0, mine = ~0ull, extra = ~0ull;
     for (int t = 0; t < M; ++t) {
         unsigned long long best = ~0ull;
-        for (int q = lane; q < cnt; q += 32) {
-            const unsigned long long kq = keys[q];
+        for (int q = lane; q < nsel; q += 32) {
+            const unsigned long long kq = sel[q];
             if ((t == 0 || kq > prev) && kq < best) best = kq;
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -575,6 +610,105 @@ __global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__rest
         for (unsigned t = 0; t < nSx; ++t) dst[t] = pairs[t].i;
         if (nSx == 1) { dst[1] = pairs[0].i; out_count[r] = 2; } else out_count[r] = nSx;
     }
+}
+
+// General path: one warp per reference patch, either all of them (list == nullptr) or the ones k_bm_select_fast deferred.
+__global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__restrict__ s_at, const float *__restrict__ s_mir,
+                                                  unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx,
+                                                  const unsigned *__restrict__ list, const unsigned *__restrict__ list_count)
+{
+    extern __shared__ unsigned long long keys[];      // up to Ns*Ns entries, later reused as LfPair[]
+    const int n = list ? (int) *list_count : g.R;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        lf_bm_select_one(g, list ? (int) list[i] : i, keys, s_at, s_mir, out_count, out_idx);
+        __syncwarp();
+    }
+}
+
+// Fast path: one thread per reference patch (coalesced reads of the sampled sums, lane <-> r), the NM = N + 1 smallest
+// (distance, push order) keys kept sorted in registers. Without an exact float tie among the selected distances the
+// reference's partial_sort returns exactly these, in this order; reference patches with a tie are deferred to k_bm_select.
+template <int NM>
+__global__ void __launch_bounds__(128) k_bm_select_fast(SelGeom g, const float *__restrict__ s_at, const float *__restrict__ s_mir,
+                                                        unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx,
+                                                        unsigned *__restrict__ list, unsigned *__restrict__ list_count)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.R) return;
+    const int k_r = g.rows[r / g.nc] * g.w + g.cols[r % g.nc];
+    const int Ns = g.Ns, nSim = g.nSim;
+    const size_t R = (size_t) g.R;
+    unsigned long long top[NM];
+#pragma unroll
+    for (int t = 0; t < NM; ++t) top[t] = ~0ull;
+    int cnt = 0;
+    auto offer = [&](float test, float val, unsigned o) {
+        if (test < g.threshold) {
+            ++cnt;
+            const unsigned long long key = ((unsigned long long) lf_fkey(val + 0.0f) << 32) | o;
+            if (key < top[NM - 1]) {
+                top[NM - 1] = key;
+#pragma unroll
+                for (int t = NM - 1; t > 0; --t) {
+                    const unsigned long long a = top[t - 1], b = top[t];
+                    const bool sw = b < a;
+                    top[t - 1] = sw ? b : a;
+                    top[t] = sw ? a : b;
+                }
+            }
+        }
+    };
+    // candidates in the reference's push order: for dj { di = 0..nSim ; di = -nSim..-1 }
+    unsigned o = 0;
+    for (int djx = 0; djx < Ns; ++djx) {
+        const float *pa = s_at + (size_t) djx * R + r;
+        int rem = 0;
+        for (; rem + 4 <= nSim + 1; rem += 4, o += 4) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(pa + (size_t) (rem + u) * Ns * R);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) offer(v[u], v[u], o + u);
+        }
+        for (; rem <= nSim; ++rem, ++o) { const float v = __ldg(pa + (size_t) rem * Ns * R); offer(v, v, o); }
+        // di = -nSim + j, j = 0..nSim-1: sums of the mirrored pair, stored at plane (Ns-1-djx) + (nSim - j) * Ns
+        const size_t mb = (size_t) (Ns - 1 - djx) * R + r;
+        int j = 0;
+        for (; j + 4 <= nSim; j += 4, o += 4) {
+            float t4[4], v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const size_t off = mb + (size_t) (nSim - (j + u)) * Ns * R;
+                t4[u] = __ldg(s_at + off);
+                v4[u] = __ldg(s_mir + off);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) offer(t4[u], v4[u], o + u);
+        }
+        for (; j < nSim; ++j, ++o) {
+            const size_t off = mb + (size_t) (nSim - j) * Ns * R;
+            offer(__ldg(s_at + off), __ldg(s_mir + off), o);
+        }
+    }
+    unsigned nSx;
+    if ((unsigned) g.N > (unsigned) cnt) { nSx = 1; while (nSx * 2 <= (unsigned) cnt) nSx *= 2; } else nSx = g.N;
+    unsigned *dst = out_idx + (size_t) r * (g.N + 1);
+    if (cnt == 0) { dst[0] = k_r; dst[1] = k_r; out_count[r] = 2; return; }
+    const int M = min(cnt, (int) nSx + 1);
+    bool tie = false;
+#pragma unroll
+    for (int t = 0; t + 1 < NM; ++t)
+        if (t + 1 < M && (unsigned) (top[t] >> 32) == (unsigned) (top[t + 1] >> 32)) tie = true;
+    if (tie) { list[atomicAdd(list_count, 1u)] = (unsigned) r; return; }
+    auto idx_of = [&](unsigned oo) -> unsigned {
+        const int djx = (int) oo / Ns, rem = (int) oo - djx * Ns;
+        const int di = rem <= nSim ? rem : -nSim + (rem - nSim - 1);
+        return (unsigned) (k_r + di * g.w + (djx - nSim));
+    };
+#pragma unroll
+    for (int t = 0; t < NM - 1; ++t)
+        if (t < (int) nSx) dst[t] = idx_of((unsigned) (top[t] & 0xffffffffu));
+    if (nSx == 1) { dst[1] = idx_of((unsigned) (top[0] & 0xffffffffu)); out_count[r] = 2; } else out_count[r] = nSx;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -118,7 +118,7 @@ struct lfbm5d_ctx {
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist;
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
@@ -454,8 +454,27 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         SelGeom sg{};
         sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = Ns; sg.N = pc.N; sg.R = R; sg.nc = nc; sg.threshold = threshold;
         sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
-        LAUNCH(ctx, k_bm_select, R, 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
-               ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+        void (*kfast)(SelGeom, const float *, const float *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
+        switch (pc.N) {
+            case 2: kfast = k_bm_select_fast<3>; break;
+            case 4: kfast = k_bm_select_fast<5>; break;
+            case 8: kfast = k_bm_select_fast<9>; break;
+            case 16: kfast = k_bm_select_fast<17>; break;
+            case 32: kfast = k_bm_select_fast<33>; break;
+            default: break;
+        }
+        if (kfast) {
+            // one thread per reference patch; the few with an exact float tie among the selected distances go to the warp kernel
+            if (ctx->tielist.ensure((R + 1) * 4)) return 1;
+            unsigned *tl = ctx->tielist.as<unsigned>();
+            CK(cudaMemsetAsync(tl + R, 0, 4, ctx->stream));
+            LAUNCH(ctx, kfast, (R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(),
+                   ctx->bmidx.as<unsigned>(), tl, tl + R);
+            LAUNCH(ctx, k_bm_select, std::min<size_t>(R, (size_t) ctx->num_sms * 16), 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(),
+                   ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl, (const unsigned *) (tl + R));
+        } else
+            LAUNCH(ctx, k_bm_select, R, 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
+                   ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) nullptr, (const unsigned *) nullptr);
     } else {
         LAUNCH(ctx, k_bm_identity, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) pc.wb, R, (int) pc.N,
                ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
@@ -831,7 +850,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
