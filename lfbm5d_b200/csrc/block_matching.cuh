@@ -717,9 +717,10 @@ __global__ void __launch_bounds__(128) k_bm_select_fast(SelGeom g, const float *
 // downstream (core:294, 310, 503, 510); the full std::sort is emulated only where the minimum is tied.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_stereo_argmin(const float *__restrict__ sums, size_t plane_stride, int w, int nDisp, int lo, int row_end, int col_end,
-                                int nstrips, int SR, float threshold, unsigned *__restrict__ out_first, unsigned char *__restrict__ out_shape)
+                                int nstrips, int SR, float threshold, unsigned *__restrict__ out_first, unsigned char *__restrict__ out_shape,
+                                unsigned slot, uint2 *__restrict__ tie_list, unsigned *__restrict__ tie_count)
 {
-    const int Ns = 2 * nDisp + 1, np = Ns * Ns;
+    const int Ns = 2 * nDisp + 1;
     const size_t total = (size_t) nstrips * SR * 32;
     for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
         const int lane = (int) (t & 31);
@@ -736,19 +737,43 @@ __global__ void k_stereo_argmin(const float *__restrict__ sums, size_t plane_str
                 if (c == 0 || v < best) { best = v; nmin = 1; amin = c; }
                 else if (v == best) nmin++;
             }
-        unsigned first = (unsigned) (k_r + (amin % Ns - nDisp) * w + (amin / Ns - nDisp));
-        if (nmin > 1) {
-            LfPair td[LF_MAXNS2];
-            c = 0;
-            for (int djx = 0; djx < Ns; ++djx)
-                for (int dix = 0; dix < Ns; ++dix, ++c) {
-                    td[c].d = sums[(size_t) (djx + dix * Ns) * plane_stride + t];
-                    td[c].i = (unsigned) (k_r + (dix - nDisp) * w + (djx - nDisp));
-                }
-            lfs_sort(td, np);
-            first = td[0].i;
-        }
-        out_first[k_r] = first;
+        out_first[k_r] = (unsigned) (k_r + (amin % Ns - nDisp) * w + (amin / Ns - nDisp));
         out_shape[k_r] = best < threshold ? 1 : 0;
+        // a tied minimum: element [0] of the reference's std::sort depends on the sort's moves; k_stereo_ties redoes these
+        if (nmin > 1) tie_list[atomicAdd(tie_count, 1u)] = make_uint2(slot, (unsigned) t);
+    }
+}
+
+// Positions whose minimum distance is tied (mirror-symmetric borders, flat regions): one thread per listed position runs the
+// re-implemented libstdc++ std::sort on the (distance, index) pairs in the reference's push order (core:3590-3606).
+struct TieGeom {
+    size_t plane_stride;
+    int w, nDisp, lo, nstrips, SR;
+    unsigned plane;                     // w * h
+    int sai[LF_MAXA];                   // window slot of every stereo slot
+};
+__global__ void k_stereo_ties(TieGeom g, const float *__restrict__ sums, const uint2 *__restrict__ tie_list, const unsigned *__restrict__ tie_count,
+                              unsigned *__restrict__ first)
+{
+    const int Ns = 2 * g.nDisp + 1, np = Ns * Ns;
+    const unsigned n = *tie_count;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint2 en = tie_list[e];
+        const size_t t = en.y;
+        const int lane = (int) (t & 31);
+        const size_t rs = t >> 5;
+        const int strip = (int) (rs / g.SR), sidx = (int) (rs - (size_t) strip * g.SR);
+        const int i = g.lo + sidx - lane, j = g.lo + (strip << 5) + lane;
+        const int k_r = i * g.w + j;
+        const float *sp = sums + (size_t) en.x * np * g.plane_stride + t;
+        LfPair td[LF_MAXNS2];
+        int c = 0;
+        for (int djx = 0; djx < Ns; ++djx)
+            for (int dix = 0; dix < Ns; ++dix, ++c) {
+                td[c].d = sp[(size_t) (djx + dix * Ns) * g.plane_stride];
+                td[c].i = (unsigned) (k_r + (dix - g.nDisp) * g.w + (djx - g.nDisp));
+            }
+        lfs_sort(td, np);
+        first[(size_t) g.sai[en.x] * g.plane + k_r] = td[0].i;
     }
 }

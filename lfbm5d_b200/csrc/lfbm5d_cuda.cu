@@ -118,7 +118,7 @@ struct lfbm5d_ctx {
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist;
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
@@ -479,11 +479,24 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
         LAUNCH(ctx, k_bm_identity, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) pc.wb, R, (int) pc.N,
                ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
     }
-    for (int s = 0; s < slot; s++) {
-        const int st = stereo_sai[s];
-        LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
-               (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
-               ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane);
+    if (slot > 0) {
+        // every position could be tied (a flat light field): room for all of them
+        if (ctx->stielist.ensure(((size_t) slot * st_stride + 1) * 8)) return 1;
+        uint2 *sl = ctx->stielist.as<uint2>();
+        unsigned *sc = reinterpret_cast<unsigned *>(sl + (size_t) slot * st_stride);
+        CK(cudaMemsetAsync(sc, 0, 4, ctx->stream));
+        TieGeom tg{};
+        tg.plane_stride = st_stride; tg.w = (int) pc.wb; tg.nDisp = (int) pc.nDisp; tg.lo = st_lo; tg.nstrips = st_strips; tg.SR = st_SR;
+        tg.plane = (unsigned) plane;
+        for (int s = 0; s < slot; s++) {
+            const int st = stereo_sai[s];
+            tg.sai[s] = st;
+            LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
+                   (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
+                   ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned) s, sl, sc);
+        }
+        LAUNCH(ctx, k_stereo_ties, ctx->num_sms * 8, 64, 0, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
+               ctx->first.as<unsigned>());
     }
     if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure(R * 2)) return 1;
     LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) R, (int) pc.wb, (unsigned) plane,
@@ -850,7 +863,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
