@@ -810,6 +810,7 @@ typedef struct {
     float cnsa[MAXASW * MAXASW], cnisa[MAXASW * MAXASW];
     float sigma_table[3];
     float lambda;
+    int partial;          /* `pst != cst` branch: 2-D transforms of the local variants (core:1715, :1756, :1822) */
 } pass_ctx;
 
 /* 2-D spatial transform of the k x k patch of `plane` at flat position pos (core:1679 / bm3d.cpp:705 / :831);
@@ -817,7 +818,9 @@ typedef struct {
 static void t2d_forward(const pass_ctx *cx, const float *plane, unsigned w_b, unsigned pos, float *out)
 {
     const unsigned k = cx->k, k2 = cx->k2;
-    if (pos % w_b >= w_b - k) { for (unsigned i = 0; i < k2; i++) out[i] = 0.0f; return; }
+    /* the row-band variants fill columns j < w_b - k only (core:1697): column w_b - k stays zero; the local variants of the
+       partial-window branch write every column they read (core:1735) */
+    if (!cx->partial && pos % w_b >= w_b - k) { for (unsigned i = 0; i < k2; i++) out[i] = 0.0f; return; }
     float patch[1024];
     for (unsigned p = 0; p < k; p++)
         for (unsigned q = 0; q < k; q++) patch[p * k + q] = plane[pos + p * w_b + q];
@@ -1082,6 +1085,29 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
              unsigned tau_2D, unsigned tau_4D, unsigned tau_5D,
              unsigned *dbg_count, unsigned *dbg_idx, unsigned *dbg_first, unsigned *dbg_shape)
 {
+    return orc_pass_ex(step, sigma, lambda, noisy_sym, basic_sym, num_sym, den_sym, mask_asw, procSAI_asw, pst, pst, asw, w_b, h_b, chnls,
+                       nSim, nDisp, k, N, p, color_space, tau_2D, tau_4D, tau_5D, dbg_count, dbg_idx, dbg_first, dbg_shape);
+}
+
+/* utilities_LF.cpp:1000-1016 */
+static int patch_denoised(const float *den0, unsigned p_idx, unsigned w_b, unsigned k)
+{
+    for (unsigned p = 0; p < k; p++)
+        for (unsigned q = 0; q < k; q++)
+            if (den0[p_idx + p * w_b + q] == 0.0) return 0;
+    return 1;
+}
+
+/* One core call. cst = window slot of the SAI the window was centred on; pst == cst is the full-grid branch (core:223-530 /
+   :986-1331), pst != cst the partial-window branch (core:531-821 / :1332-1658): only the grid patches of SAI pst that still
+   contain a pixel with den == 0 are processed (den-aware ind_initialize, utilities_LF.cpp:1031-1099), block matching is the
+   same computation restricted to them (core:3631-3788, :3806-3945) and the 2-D transforms are the local variants. */
+int orc_pass_ex(int step, float sigma, float lambda, const float *noisy_sym, const float *basic_sym, float *num_sym, float *den_sym,
+                const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned cst, unsigned pst, unsigned asw, unsigned w_b, unsigned h_b,
+                unsigned chnls, unsigned nSim, unsigned nDisp, unsigned k, unsigned N, unsigned p, unsigned color_space,
+                unsigned tau_2D, unsigned tau_4D, unsigned tau_5D,
+                unsigned *dbg_count, unsigned *dbg_idx, unsigned *dbg_first, unsigned *dbg_shape)
+{
     const unsigned A = asw * asw, n = nSim + nDisp, k2 = k * k;
     const size_t plane = (size_t) w_b * h_b;
     if (asw > MAXASW || chnls > 3 || k2 > 1024 || N > 64) return 1;
@@ -1104,6 +1130,18 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
 
     unsigned *rows = (unsigned *) malloc(sizeof(unsigned) * (h_b + 2)), *cols = (unsigned *) malloc(sizeof(unsigned) * (w_b + 2));
     const unsigned nr = orc_ind_initialize(rows, h_b - k + 1, n, p), nc = orc_ind_initialize(cols, w_b - k + 1, n, p);
+    cx->partial = pst != cst;
+    unsigned char *act = (unsigned char *) malloc((size_t) nr * nc);
+    {
+        size_t nact = 0;
+        const float *den0 = den_sym + (size_t) pst * chnls * plane;
+        for (unsigned a = 0; a < nr; a++)
+            for (unsigned b = 0; b < nc; b++) {
+                act[(size_t) a * nc + b] = cx->partial ? !patch_denoised(den0, rows[a] * w_b + cols[b], w_b, k) : 1;
+                nact += act[(size_t) a * nc + b];
+            }
+        if (nact == 0) { free(act); free(rows); free(cols); free(cx); return 0; }   /* core:160-165 */
+    }
 
     /* running estimate, channel 0 only (the only one block matching reads): core:169 / :937 */
     const float *sub = step == 1 ? noisy_sym : basic_sym;
@@ -1146,6 +1184,7 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
 #else
             const int tid = 0;
 #endif
+            if (!act[(size_t) a * nc + b]) continue;
             process_group(cx, step, noisy_sym, basic_sym, w_b, h_b, mask_asw, pst, i_r * w_b + cols[b],
                           bm_count, bm_idx, maxN, st_first, st_shape, &gos[b], scr[tid]);
         }
@@ -1153,6 +1192,7 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
             if (procSAI_asw[st]) continue;
             for (unsigned b = 0; b < nc; b++) {
                 const group_out *go = &gos[b];
+                if (!act[(size_t) a * nc + b]) continue;
                 if (!(tau_4D != ORC_SADCT || st == pst || go->shape[st])) continue;
                 for (unsigned c = 0; c < chnls; c++) {
                     float *num = num_sym + ((size_t) st * chnls + c) * plane;
@@ -1173,7 +1213,7 @@ int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const 
     }
     for (unsigned b = 0; b < nc; b++) free(gos[b].Z);
     for (int t = 0; t < nt; t++) free(scr[t]);
-    free(scr); free(gos); free(rows); free(cols); free(cx);
+    free(scr); free(gos); free(rows); free(cols); free(cx); free(act);
     if (!dbg_count) free(bm_count);
     if (!dbg_idx) free(bm_idx);
     if (!dbg_first) free(st_first);
@@ -1259,11 +1299,20 @@ static int run_step(int step, float sigma, float lambda, float *noisy, const uns
         const unsigned max_unproc = n_unproc;
         unsigned calls = 0;
         while (n_unproc && rc == 0) {
-            unsigned pst_asw;
+            unsigned pst_asw = 0;
             if (n_unproc == max_unproc && mask_asw[cst_asw]) pst_asw = cst_asw;
-            else { rc = 2; break; }   /* `pst != cst` partial-window path (core:531-821): not restated yet */
-            rc = orc_pass(step, sigma, lambda, nsym, bsym, numsym, densym, mask_asw, proc_asw, pst_asw, asw, w_b, h_b, chnls,
-                          nSim, nDisp, k, N, p, color_space, tau_2D, tau4, tau_5D, NULL, NULL, NULL, NULL);
+            else {   /* the unprocessed SAI of the window with the most zero weights in its padded den, ties to the highest slot */
+                int best = -1;
+                for (unsigned a = 0; a < Aw; a++) {
+                    if (proc_asw[a]) continue;
+                    int z = 0;
+                    const float *d = densym + a * each_b;
+                    for (size_t t = 0; t < each_b; t++) z += d[t] == 0.0;
+                    if (z >= best) { pst_asw = a; best = z; }
+                }
+            }
+            rc = orc_pass_ex(step, sigma, lambda, nsym, bsym, numsym, densym, mask_asw, proc_asw, cst_asw, pst_asw, asw, w_b, h_b, chnls,
+                             nSim, nDisp, k, N, p, color_space, tau_2D, tau4, tau_5D, NULL, NULL, NULL, NULL);
             if (rc) break;
             calls++;
             proc_asw[pst_asw] += 1;

@@ -89,7 +89,7 @@ def bm_stereo(img1, img2, k, nHW, nDisp, tau):
 
 
 def run_pass(step, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, asw, sigma, lam, nSim, nDisp, k, N, p,
-             tau2, tau4, tau5, cs=OPP, debug=False):
+             tau2, tau4, tau5, cs=OPP, debug=False, cst=None):
     A, Cn, hb, wb = noisy_sym.shape
     num = f32(num_sym).copy()
     den = f32(den_sym).copy()
@@ -99,8 +99,8 @@ def run_pass(step, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, asw,
     if debug:
         dbg = [np.zeros(hb * wb, np.uint32), np.zeros((hb * wb, N + 1), np.uint32),
                np.zeros((A, hb * wb), np.uint32), np.zeros((A, hb * wb), np.uint32)]
-    rc = lib().orc_pass(step, C.c_float(sigma), C.c_float(lam), fp(ns), fp(bs), fp(num), fp(den), up(u32(mask)), up(u32(proc)),
-                        pst, asw, wb, hb, Cn, nSim, nDisp, k, N, p, cs, tau2, tau4, tau5, *[up(d) for d in dbg])
+    rc = lib().orc_pass_ex(step, C.c_float(sigma), C.c_float(lam), fp(ns), fp(bs), fp(num), fp(den), up(u32(mask)), up(u32(proc)),
+                           pst if cst is None else cst, pst, asw, wb, hb, Cn, nSim, nDisp, k, N, p, cs, tau2, tau4, tau5, *[up(d) for d in dbg])
     assert rc == 0, rc
     return (num, den, dbg) if debug else (num, den)
 
