@@ -103,6 +103,11 @@ void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned max_passes);
 int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
                       float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw,
                       unsigned pst, unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
+/* Same with the slot the window was centred on: pst != cst runs the partial-window branch (bm5d_core_processing.cpp:531-821 /
+ * :1332-1658; only the grid patches of SAI pst that still hold a pixel without weight are processed). */
+int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
+                         float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned cst,
+                         unsigned pst, unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
 /* Block matching alone on one padded channel-0 plane (host pointers). */
 int lfbm5d_debug_bm_self(lfbm5d_ctx *ctx, const float *img, unsigned w_b, unsigned h_b, unsigned k, unsigned N, unsigned nHW,
                          unsigned nSim, unsigned p, float tauMatch, unsigned *out_count, unsigned *out_idx);

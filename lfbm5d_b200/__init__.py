@@ -43,7 +43,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset_stats", "lfbm5d_get_stats",
            "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
-           "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_bm_self",
+           "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_pass_ex", "lfbm5d_debug_bm_self",
            "lfbm5d_debug_bm_stereo", "lfbm5d_debug_schedule"]
 
 _lib = None
@@ -180,7 +180,7 @@ class LFBM5D(object):
             raise RuntimeError("lfbm5d_step2_device: " + self.error())
 
     # -- parity/debug: one window pass on padded host buffers --------------------------------------
-    def debug_pass(self, step, prm, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, debug=False):
+    def debug_pass(self, step, prm, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, debug=False, cst=None):
         A, Cn, hb, wb = noisy_sym.shape
         ns = np.ascontiguousarray(noisy_sym, np.float32)
         bs = None if basic_sym is None else np.ascontiguousarray(basic_sym, np.float32)
@@ -190,9 +190,10 @@ class LFBM5D(object):
         if debug:
             dbg = [np.zeros(hb * wb, np.uint32), np.zeros((hb * wb, prm.N + 1), np.uint32),
                    np.zeros((A, hb * wb), np.uint32), np.zeros((A, hb * wb), np.uint32)]
-        rc = self.lib.lfbm5d_debug_pass(self.ctx, int(step), C.byref(prm), _fp(ns), None if bs is None else _fp(bs),
-                                        _fp(num), _fp(den), _up(np.ascontiguousarray(mask, np.uint32)),
-                                        _up(np.ascontiguousarray(proc, np.uint32)), int(pst), *[_up(d) for d in dbg])
+        rc = self.lib.lfbm5d_debug_pass_ex(self.ctx, int(step), C.byref(prm), _fp(ns), None if bs is None else _fp(bs),
+                                           _fp(num), _fp(den), _up(np.ascontiguousarray(mask, np.uint32)),
+                                           _up(np.ascontiguousarray(proc, np.uint32)), int(pst if cst is None else cst), int(pst),
+                                           *[_up(d) for d in dbg])
         if rc != 0:
             raise RuntimeError("lfbm5d_debug_pass: " + self.error())
         return (num, den, dbg) if debug else (num, den)

@@ -19,6 +19,8 @@ struct GroupArgs {
     float *wbuf;                                  // [R][C]
     const unsigned short *gmask;                  // [R] bit st = SAI st takes part in the group's angular shape (k_group_masks)
     const struct GroupShape *shape_lut;           // [2^A] SA-DCT index tables per shape (host-built, core:300-330)
+    const unsigned char *act;                     // partial-window branch: [R] 1 = reference patch still to be processed; nullptr = all
+    int partial;                                  // pst != cst: local 2-D variants (no zero column, core:1735)
     unsigned *ent;                                // [A][R*N] (y << 16 | x) of every patch that is aggregated, else LF_NOENT
     int R;
     LfWindow win;
@@ -395,13 +397,21 @@ __device__ __forceinline__ void lf_t2d(float *B, int npatch, const GroupArgs &g,
 // Per-group set-up shared by the group kernels (core:277-299, :486-503): SA-DCT shape of the group, source offset of every
 // gathered patch (ZB: patches that read as zeros point at the zero block behind the window buffers, else szero marks them),
 // and the aggregation entries: (y << 16 | x) of every patch that k_aggregate has to add, LF_NOENT otherwise.
+// Returns false (after marking the group's entries empty) for reference patches the partial-window branch skips.
 template <bool ZB>
-__device__ __forceinline__ void lf_group_setup(const GroupArgs &g, int r, int nSx, GroupShape &sh, unsigned *sofs, unsigned char *szero)
+__device__ __forceinline__ bool lf_group_setup(const GroupArgs &g, int r, int nSx, GroupShape &sh, unsigned *sofs, unsigned char *szero)
 {
     __shared__ unsigned s_yx[LF_MAXN * LF_MAXA];
     const int A = g.A, w = g.w, k = g.k;
     const int tid = threadIdx.x, nt = blockDim.x;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
+    if (g.act && !g.act[r]) {        // den-aware ind_initialize (utilities_LF.cpp:1031-1099): every pixel of the patch already has a weight
+        for (int t = tid; t < g.N * A; t += nt) {
+            const int n = t / A, st = t - n * A;
+            g.ent[(size_t) st * g.R * g.N + (size_t) r * g.N + n] = LF_NOENT;
+        }
+        return false;
+    }
     if (tid >= nt - 32) {        // the last warp copies the group's SA-DCT tables, beside the offset loop of the first warps
         const unsigned *src = reinterpret_cast<const unsigned *>(g.shape_lut + g.gmask[r]);
         unsigned *dst = reinterpret_cast<unsigned *>(&sh);
@@ -412,7 +422,7 @@ __device__ __forceinline__ void lf_group_setup(const GroupArgs &g, int r, int nS
         const unsigned ind = g.bm_idx[(size_t) r * (g.N + 1) + n];
         const unsigned pv = (st == g.pst) ? ind : (g.win.mask[st] ? g.first[(size_t) st * plane + ind] : 0u);
         const unsigned py = pv / (unsigned) w, px = pv - py * (unsigned) w;
-        const bool zero = !g.win.mask[st] || (int) px >= w - k;       // empty SAI, or column w-k (core:1697)
+        const bool zero = !g.win.mask[st] || (!g.partial && (int) px >= w - k);       // empty SAI, or column w-k (core:1697)
         if (ZB) sofs[t] = zero ? (unsigned) A * (unsigned) g.C * plane : (unsigned) st * (unsigned) g.C * plane + pv;
         else { sofs[t] = (unsigned) st * (unsigned) g.C * plane + pv; szero[t] = zero ? 1 : 0; }
         s_yx[t] = (py << 16) | px;
@@ -424,6 +434,22 @@ __device__ __forceinline__ void lf_group_setup(const GroupArgs &g, int r, int nS
         const bool on = n < nSx && !g.win.proc[st] && !(g.tau_4D == 6 && st != g.pst && !sh.mask[st]);
         g.ent[(size_t) st * g.R * g.N + (size_t) r * g.N + n] = on ? s_yx[t] : LF_NOENT;
     }
+    return true;
+}
+
+// partial-window branch: reference patches of the grid that still contain a pixel without weight in SAI pst (channel 0)
+__global__ void k_active_refs(const float *__restrict__ den0, const int *__restrict__ rows, const int *__restrict__ cols, int nc, int R, int w,
+                              int k, unsigned char *__restrict__ act, unsigned *__restrict__ count)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float *pp = den0 + (size_t) rows[r / nc] * w + cols[r % nc];
+    bool open = false;
+    for (int p = 0; p < k && !open; ++p)
+        for (int q = 0; q < k; ++q)
+            if (pp[p * w + q] == 0.0f) { open = true; break; }
+    act[r] = open ? 1 : 0;
+    if (open) atomicAdd(count, 1u);
 }
 
 // bit st of gmask[r]: SAI st belongs to the angular shape of reference patch r (core:300-312)
@@ -465,7 +491,7 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     const int p = pq >> g.log2k, q = pq & (k - 1);
     const int poff = p * RS + q;
     const int npatch = nSx * A;
-    lf_group_setup<false>(g, r, nSx, sh, sofs, szero);
+    if (!lf_group_setup<false>(g, r, nSx, sh, sofs, szero)) return;
     const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
     float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
 
@@ -661,7 +687,7 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
     const int nSx = (int) g.bm_count[r];
     const int lg = 31 - __clz(nSx);
     const int pq = tid, p = pq >> 4, q = pq & 15;
-    lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr);
+    if (!lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr)) return;
     const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
     float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
     for (int c = 0; c < g.C; ++c) {

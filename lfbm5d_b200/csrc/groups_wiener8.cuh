@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
     const int nSx = (int) g.bm_count[r];
     const int npatch = nSx * A;
 
-    lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr);
+    if (!lf_group_setup<true>(g, r, nSx, sh, sofs, nullptr)) return;
     const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
 
     // per-thread constants of the phases

@@ -118,7 +118,7 @@ struct lfbm5d_ctx {
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist, act;
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
@@ -352,8 +352,23 @@ int ensure_shape_lut(lfbm5d_ctx *ctx, unsigned asw)
 }
 
 // One core call on the padded device buffers of the window (nsym/bsym/numsym/densym/est0 already filled).
-int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
+// cst = slot the window was centred on: pst != cst is the partial-window branch (core:531-821 / :1332-1658).
+int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, int cst = -1)
 {
+    const bool partial = cst >= 0 && cst != pst;
+    if (partial) {
+        const size_t Rr = pc.rows.size() * pc.cols.size();
+        if (ctx->act.ensure(Rr + 8)) return 1;
+        unsigned *cnt = reinterpret_cast<unsigned *>(ctx->act.as<unsigned char>() + ((Rr + 3) & ~(size_t) 3));
+        CK(cudaMemsetAsync(cnt, 0, 4, ctx->stream));
+        LAUNCH(ctx, k_active_refs, (unsigned) ((Rr + 255) / 256), 256, 0,
+               ctx->densym.as<float>() + (size_t) pst * pc.C * pc.wb * pc.hb, ctx->rows.as<int>(), ctx->cols.as<int>(), (int) pc.cols.size(), (int) Rr,
+               (int) pc.wb, (int) pc.k, ctx->act.as<unsigned char>(), cnt);
+        unsigned h = 0;
+        CK(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (h == 0) return 0;       // nothing left to denoise in this SAI (core:160-165)
+    }
     const size_t plane = (size_t) pc.wb * pc.hb;
     const int nr = (int) pc.rows.size(), nc = (int) pc.cols.size(), R = nr * nc;
     const int Ns = 2 * (int) pc.nSim + 1, nself = pc.N > 1 ? ((int) pc.nSim + 1) * Ns : 0;
@@ -506,6 +521,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst)
     // ---- groups ----
     GroupArgs ga{};
     ga.gmask = ctx->gmask.as<unsigned short>(); ga.shape_lut = ctx->shape_lut.as<GroupShape>();
+    ga.act = partial ? ctx->act.as<unsigned char>() : nullptr; ga.partial = partial ? 1 : 0;
     ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
     ga.pst = pst; ga.nc = nc;
     // row padding removes the shared-memory bank conflicts of the 2-D passes (3 CTAs/SM without it measured slower)
@@ -677,11 +693,32 @@ int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_nois
         const unsigned max_unproc = n_unproc;
         unsigned calls = 0;
         while (n_unproc) {
-            unsigned pst_asw;
+            unsigned pst_asw = 0;
             if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
-            else return fail("window not covered after its first SAI: the `pst != cst` partial-window path "
-                             "(bm5d_core_processing.cpp:531-821) is not implemented in this build");
-            if (run_pass(ctx, pc, win, (int) pst_asw)) return 1;
+            else {
+                // bm5d.cpp:318-333: the unprocessed SAI of the window with the most zero weights in its padded den (all channels),
+                // ties to the highest slot; the reference keeps the count in an int
+                const size_t each_b = (size_t) C * pc.wb * pc.hb;
+                if (ctx->counters.ensure((Aw + 8) * 8)) return 1;
+                counters = ctx->counters.as<unsigned long long>();
+                CK(cudaMemsetAsync(counters, 0, Aw * 8, ctx->stream));
+                for (unsigned a = 0; a < Aw; a++)
+                    if (win.proc[a] == 0)
+                        LAUNCH(ctx, k_count_zero, grid_for(ctx, each_b), 256, 0, ctx->densym.as<float>() + a * each_b, each_b, counters + a);
+                std::vector<unsigned long long> hz(Aw);
+                CK(cudaMemcpyAsync(hz.data(), counters, Aw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                long long best = -1;
+                for (unsigned a = 0; a < Aw; a++) {
+                    if (win.proc[a]) continue;
+                    const long long z = (long long) (int) hz[a];
+                    if (z >= best) { pst_asw = a; best = z; }
+                }
+            }
+            if (calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937)
+                LAUNCH(ctx, k_est0, grid_for(ctx, pc.A * (size_t) pc.wb * pc.hb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
+                       ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (size_t) pc.wb * pc.hb, (int) pc.C);
+            if (run_pass(ctx, pc, win, (int) pst_asw, (int) cst_asw)) return 1;
             calls++;
             win.proc[pst_asw] += 1;
             proc[win.st[pst_asw]] += 1;
@@ -863,7 +900,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
@@ -951,6 +988,14 @@ int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const f
                       float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned pst,
                       unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape)
 {
+    return lfbm5d_debug_pass_ex(ctx, step, p, noisy_sym, basic_sym, num_sym_io, den_sym_io, mask_asw, procSAI_asw, pst, pst, out_count, out_idx,
+                                out_first, out_shape);
+}
+
+int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
+                         float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned cst, unsigned pst,
+                         unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape)
+{
     if (!ctx || !noisy_sym || !num_sym_io || !den_sym_io || !mask_asw || !procSAI_asw) return fail("null argument");
     if (step != 1 && step != 2) return fail("step must be 1 or 2");
     if (step == 2 && !basic_sym) return fail("step 2 needs the basic estimate");
@@ -975,7 +1020,8 @@ int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const f
     CK(cudaMemsetAsync(ctx->shape.p, 0, pc.A * plane, ctx->stream));
     LAUNCH(ctx, k_est0, grid_for(ctx, pc.A * plane), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
            ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, plane, (int) pc.C);
-    if (run_pass(ctx, pc, win, (int) pst)) return 1;
+    if (cst >= pc.A) return fail("cst out of range");
+    if (run_pass(ctx, pc, win, (int) pst, (int) cst)) return 1;
     CK(cudaMemcpyAsync(num_sym_io, ctx->numsym.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(den_sym_io, ctx->densym.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -18,3 +18,12 @@ def run_inputs(tag):
     aw, H, W = {"3x3": (3, 32, 40), "5x5": (5, 24, 28)}[tag]
     clean = lfdata.synth_lf(aw, aw, H, W)
     return aw, clean, O.add_noise(clean, 25.0)
+
+
+def partial_holes(num, den):
+    """Accumulators of a first core call with the weights of SAI 1 and 6 removed in places (tests/make_golden.py)."""
+    num, den = num.copy(), den.copy()
+    num[1][:, 30:52, 28:70] = 0; den[1][:, 30:52, 28:70] = 0
+    num[1][:, 60:, :40] = 0; den[1][:, 60:, :40] = 0
+    num[6][:, :, 60:] = 0; den[6][:, :, 60:] = 0
+    return num, den

@@ -24,6 +24,15 @@ def pad_inputs(H, W, sigma, n=24):
     return clean, noisy, np.stack([O.symetrize(y[st], n) for st in range(9)])
 
 
+def partial_holes(num, den):
+    """Accumulators of a first core call with the weights of SAI 1 and 6 removed in places."""
+    num, den = num.copy(), den.copy()
+    num[1][:, 30:52, 28:70] = 0; den[1][:, 30:52, 28:70] = 0
+    num[1][:, 60:, :40] = 0; den[1][:, 60:, :40] = 0
+    num[6][:, :, 60:] = 0; den[6][:, :, 60:] = 0
+    return num, den
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     R.lib().ref_set_dct_mode(0)
@@ -65,6 +74,28 @@ def main():
         d, b2, _ = R.run_step2(nrt, b, mask, 25.0, aw, aw, 1, 16, 18, 6, 8, 4, R.DCT, R.SADCT, R.HAAR)
         out["basic_" + tag], out["noisy_rt_" + tag], out["denoised_" + tag], out["basic_rt_" + tag] = b, nrt, d, b2
     np.savez_compressed(os.path.join(GOLD, "runs.npz"), **out)
+    # 4. partial-window branch (pst != cst): one call per step on accumulators with holes, and complete grayscale runs
+    #    (several core calls per window: LF_denoised_percent stays below 100 after the first SAI when C == 1)
+    _, _, sym = pad_inputs(32, 40, 25.0)
+    z = np.zeros_like(sym)
+    out = {}
+    num, den = R.pass_step1(sym, z, z, mask, proc, 4, 4, 3, 25.0, 2.7, 18, 6, 16, 8, 4, R.ID, R.SADCT, R.HAAR)
+    basic = np.where(den != 0, num / np.where(den != 0, den, 1), sym).astype(np.float32)
+    num, den = partial_holes(num, den)
+    p2 = proc.copy(); p2[4] = 1
+    for pst in (1, 6):
+        rn, rd = R.pass_step1(sym, num, den, mask, p2, 4, pst, 3, 25.0, 2.7, 18, 6, 16, 8, 4, R.ID, R.SADCT, R.HAAR)
+        out["s1_pst%d_num" % pst], out["s1_pst%d_den" % pst] = rn[pst], rd[pst]
+        rn, rd = R.pass_step2(sym, basic, num, den, mask, p2, 4, pst, 3, 25.0, 18, 6, 8, 16, 4, R.DCT, R.SADCT, R.HAAR)
+        out["s2_pst%d_num" % pst], out["s2_pst%d_den" % pst] = rn[pst], rd[pst]
+    for tag, (aw, H, W) in {"g3x3": (3, 28, 32), "g5x5": (5, 24, 28)}.items():
+        clean = np.ascontiguousarray(lfdata.synth_lf(aw, aw, H, W)[:, :1])
+        noisy = O.add_noise(clean, 25.0)
+        m = np.ones(aw * aw)
+        b, nrt = R.run_step1(noisy, m, 25.0, 2.7, aw, aw, 1, 8, 18, 6, 16, 4, R.ID, R.SADCT, R.HAAR)
+        d, _, _ = R.run_step2(nrt, b, m, 25.0, aw, aw, 1, 16, 18, 6, 8, 4, R.DCT, R.SADCT, R.HAAR)
+        out["basic_" + tag], out["denoised_" + tag] = b, d
+    np.savez_compressed(os.path.join(GOLD, "partial.npz"), **out)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

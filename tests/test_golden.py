@@ -50,6 +50,32 @@ def test_runs_golden(oracle):
         assert np.array_equal(sch, sch2)
 
 
+def test_partial_window_golden(oracle):
+    """`pst != cst` branch (core:531-821 / :1332-1658) against vectors of the unmodified reference: single calls on
+    accumulators with holes, and a complete grayscale run (several core calls per window)."""
+    import lfdata
+    g = np.load(os.path.join(GOLD, "partial.npz"))
+    _, _, sym = gi.pad_inputs(32, 40, 25.0)
+    z = np.zeros_like(sym)
+    mask, proc = np.ones(9), np.zeros(9)
+    num, den = oracle.run_pass(1, sym, None, z, z, mask, proc, 4, 3, 25.0, 2.7, 18, 6, 16, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    basic = np.where(den != 0, num / np.where(den != 0, den, 1), sym).astype(np.float32)
+    num, den = gi.partial_holes(num, den)
+    p2 = proc.copy(); p2[4] = 1
+    for pst in (1, 6):
+        on, od = oracle.run_pass(1, sym, None, num, den, mask, p2, pst, 3, 25.0, 2.7, 18, 6, 16, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR, cst=4)
+        assert np.array_equal(on[pst], g["s1_pst%d_num" % pst]) and np.array_equal(od[pst], g["s1_pst%d_den" % pst])
+        on, od = oracle.run_pass(2, sym, basic, num, den, mask, p2, pst, 3, 25.0, 0.0, 18, 6, 8, 16, 4, oracle.DCT, oracle.SADCT, oracle.HAAR, cst=4)
+        assert np.array_equal(on[pst], g["s2_pst%d_num" % pst]) and np.array_equal(od[pst], g["s2_pst%d_den" % pst])
+    clean = np.ascontiguousarray(lfdata.synth_lf(3, 3, 28, 32)[:, :1])
+    noisy = oracle.add_noise(clean, 25.0)
+    b, nrt, sch = oracle.run_step1(noisy, np.ones(9), 25.0, 2.7, 3, 3, 1, 8, 18, 6, 16, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    assert int(sch[0][3]) == 2
+    assert np.array_equal(b, g["basic_g3x3"])
+    d, _, _, _ = oracle.run_step2(nrt, b, np.ones(9), 25.0, 3, 3, 1, 16, 18, 6, 8, 4, oracle.DCT, oracle.SADCT, oracle.HAAR)
+    assert np.array_equal(d, g["denoised_g3x3"])
+
+
 def test_schedule_pass_counts(oracle):
     """Window passes per step with an = 1: 1 (3x3), 16 (9x9) — exercised on tiny SAIs for speed."""
     import lfdata
