@@ -725,7 +725,7 @@ struct AggArgs {
 
 // K, CC: compile-time patch size / channel count (0 = take them from the arguments)
 template <int K, int CC>
-__global__ void __launch_bounds__(256) k_aggregate(AggArgs g)
+__global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
 {
     __shared__ uint2 lpos[AGG_CAP];                  // (y << 16 | x) of the patch, index of its first channel in zbuf (units of k^2)
     __shared__ float4 lw[AGG_CAP];                   // per-channel weights of its group
