@@ -588,15 +588,97 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     }
 }
 
+// ---- packed FP32x2 versions of the 3x3 angular DCT: two independent signals per register pair ----
+typedef unsigned long long lf_f2;
+
+__device__ __forceinline__ lf_f2 lf_dup(float c) { return lf_pk(c, c); }
+
+__device__ __forceinline__ void w8_dct4_fwd(lf_f2 (&v)[9], lf_f2 nz2)
+{
+    const float *T = c_tab.dctaf[2];
+    lf_f2 y[9];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            lf_f2 acc = 0ull;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) acc = lf_fma2(v[s * 3 + t], lf_dup(T[kk * 3 + t]), acc);
+            y[s * 3 + kk] = acc;
+        }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            lf_f2 acc = 0ull;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) acc = lf_fma2(y[s * 3 + t], lf_dup(T[kk * 3 + s]), acc);
+            v[kk * 3 + t] = lf_mul2(acc, lf_dup(c_tab.cn4[kk * 3 + t]), nz2);
+        }
+}
+__device__ __forceinline__ void w8_dct4_inv(lf_f2 (&v)[9], lf_f2 nz2)
+{
+    const float *T = c_tab.dctai[2];
+    lf_f2 a[9], y[9];
+#pragma unroll
+    for (int st = 0; st < 9; ++st) a[st] = lf_mul2(v[st], lf_dup(c_tab.cni4[st]), nz2);
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            lf_f2 acc = 0ull;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) acc = lf_fma2(a[s * 3 + t], lf_dup(T[kk * 3 + t]), acc);
+            y[s * 3 + kk] = acc;
+        }
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+            lf_f2 acc = 0ull;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) acc = lf_fma2(y[s * 3 + t], lf_dup(T[kk * 3 + s]), acc);
+            v[kk * 3 + t] = lf_mul2(acc, lf_dup(c_tab.coef4inv), nz2);
+        }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Register-resident variant for tau_2D = id, k = 16, step 1 (configs 1, 3, 5 of BASELINE.json): thread <-> pixel position
 // of the patch, the N x 9 samples of that position across the group live in registers through the angular DCT, the Haar
 // transform along the similar patches, the hard threshold and both inverses. No shared-memory staging, all gathers of a
 // thread in flight at once, one block reduction per channel for the weight. Same arithmetic as k_groups (bit-identical).
 // ------------------------------------------------------------------------------------------------------------
+// 3x3 angular transform of the NS vectors x[n][.]: two consecutive n per packed FP32x2 operation (SA-DCT groups: scalar path)
+template <int NS>
+__device__ __forceinline__ void lf_id_angular(float (&x)[NS][9], const GroupShape &sh, bool use_sadct, bool fwd, lf_f2 nz2)
+{
+    if (use_sadct) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            float u[9];
+#pragma unroll
+            for (int st = 0; st < 9; ++st) u[st] = x[n][st];
+            if (fwd) lf_sadct_fwd(u, sh, 3); else lf_sadct_inv(u, sh, 3);
+#pragma unroll
+            for (int st = 0; st < 9; ++st) x[n][st] = u[st];
+        }
+        return;
+    }
+    if (NS == 1) { if (fwd) lf_dct4_fwd<3>(x[0]); else lf_dct4_inv<3>(x[0]); return; }
+#pragma unroll
+    for (int h = 0; h < NS / 2; ++h) {
+        lf_f2 v[9];
+#pragma unroll
+        for (int st = 0; st < 9; ++st) v[st] = lf_pk(x[2 * h][st], x[2 * h + 1][st]);
+        if (fwd) w8_dct4_fwd(v, nz2); else w8_dct4_inv(v, nz2);
+#pragma unroll
+        for (int st = 0; st < 9; ++st) lf_upk(v[st], x[2 * h][st], x[2 * h + 1][st]);
+    }
+}
+
 template <int NS, int CC>
 __device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const unsigned *sofs, const GroupShape &sh, bool use_sadct,
-                                                     unsigned tofs, int c, int lg, float *zdst)
+                                                     unsigned tofs, int c, int lg, float *zdst, lf_f2 nz2)
 {
     constexpr int A = 9, k2 = 256;
     const int C = CC ? CC : g.C;
@@ -614,19 +696,7 @@ __device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const u
             }
         }
     }
-    if (g.tau_4D != 4) {
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-            if (use_sadct) {
-                float u[A];
-#pragma unroll
-                for (int st = 0; st < A; ++st) u[st] = x[n][st];
-                lf_sadct_fwd(u, sh, 3);
-#pragma unroll
-                for (int st = 0; st < A; ++st) x[n][st] = u[st];
-            } else lf_dct4_fwd<3>(x[n]);
-        }
-    }
+    if (g.tau_4D != 4) lf_id_angular<NS>(x, sh, use_sadct, true, nz2);
     float wpart = 0.f;
     const bool haar = g.tau_5D == 9;
     const float T = haar ? c_tab.thr[c][0] : c_tab.thr[c][lg];
@@ -652,19 +722,7 @@ __device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const u
 #pragma unroll
         for (int n = 0; n < NS; ++n) x[n][st] = v[n];
     }
-    if (g.tau_4D != 4) {
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-            if (use_sadct) {
-                float u[A];
-#pragma unroll
-                for (int st = 0; st < A; ++st) u[st] = x[n][st];
-                lf_sadct_inv(u, sh, 3);
-#pragma unroll
-                for (int st = 0; st < A; ++st) x[n][st] = u[st];
-            } else lf_dct4_inv<3>(x[n]);
-        }
-    }
+    if (g.tau_4D != 4) lf_id_angular<NS>(x, sh, use_sadct, false, nz2);
     float *zc = zdst + c * k2;
 #pragma unroll
     for (int n = 0; n < NS; ++n)
@@ -674,7 +732,7 @@ __device__ __forceinline__ float lf_group_id_channel(const GroupArgs &g, const u
 }
 
 template <int CC>
-__global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
+__global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g, unsigned long long nz2)
 {
     __shared__ GroupShape sh;
     __shared__ float red[8];
@@ -694,10 +752,10 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g)
         const unsigned tofs = (unsigned) c * plane + (unsigned) (p * w + q);
         float wpart;
         switch (nSx) {
-            case 1:  wpart = lf_group_id_channel<1, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
-            case 2:  wpart = lf_group_id_channel<2, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
-            case 4:  wpart = lf_group_id_channel<4, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
-            default: wpart = lf_group_id_channel<8, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst); break;
+            case 1:  wpart = lf_group_id_channel<1, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst, nz2); break;
+            case 2:  wpart = lf_group_id_channel<2, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst, nz2); break;
+            case 4:  wpart = lf_group_id_channel<4, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst, nz2); break;
+            default: wpart = lf_group_id_channel<8, CC>(g, sofs, sh, use_sadct, tofs, c, lg, zdst, nz2); break;
         }
         const float wsum = lf_block_sum_f(wpart, red);
         const float sg = c_tab.sigma[c];

@@ -15,10 +15,6 @@
 #define W8_ZRS 10     // filtered signal: packed (row p, row p+4) values per row pair, 4 row pairs per patch
 #define W8_ZPS 40     // packed values per patch of the filtered signal (= 16 banks mod 32 as well)
 
-typedef unsigned long long lf_f2;
-
-__device__ __forceinline__ lf_f2 lf_dup(float c) { return lf_pk(c, c); }
-
 // out[kk] = sum_j v[j] * T[kk*8 + j], ascending j from +0 (oracle DCT mode 0), on packed pairs
 __device__ __forceinline__ void w8_dct8(const lf_f2 (&v)[8], lf_f2 (&o)[8], const float *T)
 {
@@ -31,54 +27,6 @@ __device__ __forceinline__ void w8_dct8(const lf_f2 (&v)[8], lf_f2 (&o)[8], cons
     }
 }
 
-__device__ __forceinline__ void w8_dct4_fwd(lf_f2 (&v)[9], lf_f2 nz2)
-{
-    const float *T = c_tab.dctaf[2];
-    lf_f2 y[9];
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            lf_f2 acc = 0ull;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) acc = lf_fma2(v[s * 3 + t], lf_dup(T[kk * 3 + t]), acc);
-            y[s * 3 + kk] = acc;
-        }
-#pragma unroll
-    for (int t = 0; t < 3; ++t)
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            lf_f2 acc = 0ull;
-#pragma unroll
-            for (int s = 0; s < 3; ++s) acc = lf_fma2(y[s * 3 + t], lf_dup(T[kk * 3 + s]), acc);
-            v[kk * 3 + t] = lf_mul2(acc, lf_dup(c_tab.cn4[kk * 3 + t]), nz2);
-        }
-}
-__device__ __forceinline__ void w8_dct4_inv(lf_f2 (&v)[9], lf_f2 nz2)
-{
-    const float *T = c_tab.dctai[2];
-    lf_f2 a[9], y[9];
-#pragma unroll
-    for (int st = 0; st < 9; ++st) a[st] = lf_mul2(v[st], lf_dup(c_tab.cni4[st]), nz2);
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            lf_f2 acc = 0ull;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) acc = lf_fma2(a[s * 3 + t], lf_dup(T[kk * 3 + t]), acc);
-            y[s * 3 + kk] = acc;
-        }
-#pragma unroll
-    for (int t = 0; t < 3; ++t)
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-            lf_f2 acc = 0ull;
-#pragma unroll
-            for (int s = 0; s < 3; ++s) acc = lf_fma2(y[s * 3 + t], lf_dup(T[kk * 3 + s]), acc);
-            v[kk * 3 + t] = lf_mul2(acc, lf_dup(c_tab.coef4inv), nz2);
-        }
-}
 // rare shape-adaptive path: both halves through the scalar routines
 __device__ __forceinline__ void w8_sadct(lf_f2 (&v)[9], const GroupShape &sh, bool fwd)
 {

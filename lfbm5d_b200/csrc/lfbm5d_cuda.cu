@@ -542,9 +542,9 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8) {
         // register-resident path (no 2-D transform to stage); patches that contribute zeros read the zero block behind nsym
         CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-        if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga);
-        else if (pc.C == 1) k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga);
-        else k_groups_id16<0><<<R, 256, 0, ctx->stream>>>(ga);
+        if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
+        else if (pc.C == 1) k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
+        else k_groups_id16<0><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
     }
     else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR) {
         // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
