@@ -53,6 +53,24 @@ __global__ void k_color(float *lf, const unsigned *mask, unsigned nsai, size_t H
     }
 }
 
+// rt = inverse(forward(x)): what the reference leaves in LF_noisy / LF_basic after a step (bm5d.cpp:133, 711-714; not the
+// identity for OPP / YUV / YCbCr). Computed up front so that the host entry points can return it while the passes run.
+__global__ void k_roundtrip(const float *__restrict__ lf, float *__restrict__ rt, const unsigned *mask, unsigned nsai, size_t HW, unsigned cs)
+{
+    const size_t total = (size_t) nsai * HW;
+    for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
+        const unsigned st = (unsigned) (t / HW);
+        if (!mask[st]) continue;
+        const size_t px = t - (size_t) st * HW;
+        const float *b = lf + (size_t) st * 3 * HW + px;
+        float f0, f1, f2, o0, o1, o2;
+        lf_color_px(cs, true, b[0], b[HW], b[2 * HW], f0, f1, f2);
+        lf_color_px(cs, false, f0, f1, f2, o0, o1, o2);
+        float *r = rt + (size_t) st * 3 * HW + px;
+        r[0] = o0; r[HW] = o1; r[2 * HW] = o2;
+    }
+}
+
 __device__ __forceinline__ int lf_mirror(int v, int n)   // utilities.cpp:215-263 (edge pixel repeated)
 {
     return v < 0 ? -v - 1 : (v >= n ? 2 * n - 1 - v : v);

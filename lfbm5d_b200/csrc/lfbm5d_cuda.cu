@@ -113,12 +113,13 @@ struct PassCfg {
 
 struct lfbm5d_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: early device->host copies of the host entry points
+    cudaEvent_t ev_rt = nullptr;
     int num_sms = 148;
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist, act;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist, act, rt_noisy, rt_basic;
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
@@ -867,6 +868,24 @@ int download_lf(lfbm5d_ctx *ctx, const DevBuf &buf, float *const *host, const un
     return 0;
 }
 
+// The colour-round-tripped copy of an input light field (the reference's side effect on LF_noisy / LF_basic) does not depend on
+// the passes: compute it right after the upload and send it back on the second stream while the step runs. Nothing to do
+// (the caller's arrays already hold the result) without a colour transform.
+int early_roundtrip(lfbm5d_ctx *ctx, const lfbm5d_params *p, const DevBuf &src, DevBuf &rt, float *const *host, const unsigned *mask,
+                    unsigned asize, size_t each)
+{
+    if (!(p->chnls == 3 && p->color_space != LFBM5D_RGB)) return 0;
+    if (rt.ensure(asize * each * 4) || ctx->mask.ensure(asize * 4)) return 1;
+    CK(cudaMemcpyAsync(ctx->mask.p, mask, asize * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_roundtrip, grid_for(ctx, asize * (each / 3)), 256, 0, src.as<float>(), rt.as<float>(), ctx->mask.as<unsigned>(), asize, each / 3,
+           p->color_space);
+    CK(cudaEventRecord(ctx->ev_rt, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_rt, 0));
+    for (unsigned st = 0; st < asize; st++)
+        if (mask[st]) CK(cudaMemcpyAsync(host[st], rt.as<float>() + st * each, each * 4, cudaMemcpyDeviceToHost, ctx->stream2));
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -887,6 +906,8 @@ int lfbm5d_create(lfbm5d_ctx **out, int device)
     CK(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_rt, cudaEventDisableTiming));
     for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
     *out = ctx;
     return 0;
@@ -900,10 +921,12 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act, &ctx->rt_noisy, &ctx->rt_basic };
     for (auto b : all) b->release();
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_rt) cudaEventDestroy(ctx->ev_rt);
     delete ctx;
 }
 
@@ -933,9 +956,11 @@ int lfbm5d_step1(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io
     const unsigned asize = p->awidth * p->aheight;
     const size_t each = (size_t) p->width * p->height * p->chnls;
     if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || ctx->out.ensure(asize * each * 4)) return 1;
-    if (step_device(ctx, 1, p, ctx->noisy.as<float>(), nullptr, ctx->out.as<float>(), sai_mask)) return 1;
-    if (download_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each)) return 1;
-    return download_lf(ctx, ctx->out, basic_out, sai_mask, asize, each);
+    if (early_roundtrip(ctx, p, ctx->noisy, ctx->rt_noisy, noisy_io, sai_mask, asize, each)) return 1;
+    if (step_device(ctx, 1, p, ctx->noisy.as<float>(), nullptr, ctx->out.as<float>(), sai_mask)) { cudaStreamSynchronize(ctx->stream2); return 1; }
+    if (download_lf(ctx, ctx->out, basic_out, sai_mask, asize, each)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream2));
+    return 0;
 }
 
 int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, float *const *basic_io, const unsigned *sai_mask,
@@ -948,9 +973,12 @@ int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io
     const size_t each = (size_t) p->width * p->height * p->chnls;
     if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || upload_lf(ctx, ctx->basic, basic_io, sai_mask, asize, each) ||
         ctx->out.ensure(asize * each * 4)) return 1;
-    if (step_device(ctx, 2, p, ctx->noisy.as<float>(), ctx->basic.as<float>(), ctx->out.as<float>(), sai_mask)) return 1;
-    if (download_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || download_lf(ctx, ctx->basic, basic_io, sai_mask, asize, each)) return 1;
-    return download_lf(ctx, ctx->out, denoised_out, sai_mask, asize, each);
+    if (early_roundtrip(ctx, p, ctx->noisy, ctx->rt_noisy, noisy_io, sai_mask, asize, each) ||
+        early_roundtrip(ctx, p, ctx->basic, ctx->rt_basic, basic_io, sai_mask, asize, each)) return 1;
+    if (step_device(ctx, 2, p, ctx->noisy.as<float>(), ctx->basic.as<float>(), ctx->out.as<float>(), sai_mask)) { cudaStreamSynchronize(ctx->stream2); return 1; }
+    if (download_lf(ctx, ctx->out, denoised_out, sai_mask, asize, each)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream2));
+    return 0;
 }
 
 int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out,
