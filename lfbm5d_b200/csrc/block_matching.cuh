@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
                 s_bnd[warp][lane] = r < g.row_end ? lf_pk(__ldcg(&bnd_prev[r]), __ldcg(&bnd_prev[r + bB])) : 0ull;
                 __syncwarp();
                 unsigned bo = sbn;
+#pragma unroll (K == 8 ? 2 : 1)
                 for (int s = 32 * q + 1; s <= send; ++s, bo += 8) {
                     unsigned long long Lin2 = __shfl_up_sync(FULL, cur2, 1);
                     if (lane == 0) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(Lin2) : "r"(bo));
