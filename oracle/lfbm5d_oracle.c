@@ -20,6 +20,7 @@
 #define SQRT2_INV_D 0.7071067811865475
 
 static int g_dct_mode = 0;
+static int g_use_sd = 0;    /* useSD of the next orc_pass / orc_run_* calls (test infrastructure; see orc_set_use_sd) */
 static int g_bm3d = 0;      /* set while orc_run_bm3d_LF drives orc_pass: BM3D thresholds (bm3d.cpp:340, :532, :940) */
 static int g_threads = 0;
 void orc_set_dct_mode(int mode) { g_dct_mode = mode; }
@@ -1002,11 +1003,24 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
     float wt[3] = { 0.0f, 0.0f, 0.0f };
     float vo[64], ve[64];
     const float hcoef = 1.0f / (float) nSx;
+    float cn5[64], cni5[64];                     /* preProcess_5d, core:3262-3276 */
+    {
+        const float coef = (float) (SQRT2_D) / sqrt(nSx);
+        cn5[0] = (float) (SQRT2_INV_D * coef); cni5[0] = (float) (SQRT2_D);
+        for (unsigned i = 1; i < nSx; i++) { cn5[i] = coef; cni5[i] = 1.0; }
+    }
     for (unsigned pq = 0; pq < k2; pq++) {
         /* forward along n */
         for (unsigned c = 0; c < C; c++)
             for (unsigned st = 0; st < A; st++) {
-                if (nSx > 1) {
+                if (cx->tau_5D == ORC_DCT) {      /* core:2544-2556 / :2974-2989: REDFT10 of length nSx, then coef_norm_5d */
+                    for (int rep = 0; rep < step; rep++) {
+                        float *B = rep == 0 ? G : E;
+                        for (unsigned n = 0; n < nSx; n++) vo[n] = B[((size_t) (n * C + c) * k2 + pq) * A + st];
+                        r2r_1d(vo, ve, (int) nSx, 2);
+                        for (unsigned n = 0; n < nSx; n++) B[((size_t) (n * C + c) * k2 + pq) * A + st] = ve[n] * cn5[n];
+                    }
+                } else if (nSx > 1) {
                     for (unsigned n = 0; n < nSx; n++) vo[n] = G[((size_t) (n * C + c) * k2 + pq) * A + st];
                     if (cx->tau_5D == ORC_HAAR) orc_haar_forward(vo, nSx); else orc_hadamard(vo, nSx);
                     for (unsigned n = 0; n < nSx; n++) G[((size_t) (n * C + c) * k2 + pq) * A + st] = vo[n];
@@ -1023,6 +1037,7 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
             float T;
             if (g_bm3d) T = cx->lambda * sg * sqrtf((float) nSx);                 /* bm3d.cpp:940 */
             else if (cx->tau_5D == ORC_HAAR) T = cx->lambda * sg * (float) (SQRT2_D);
+            else if (cx->tau_5D == ORC_DCT) T = cx->lambda * sg * 2.0f * (float) (SQRT2_D);       /* core:2566 */
             else T = cx->lambda * sg * sqrtf((float) nSx) * (float) (SQRT2_D);
             for (unsigned st = 0; st < A; st++) {
                 if (sh.use_sadct && !sh.mask_dct[st]) continue;
@@ -1033,7 +1048,7 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
                     } else {
                         float *e = &E[((size_t) (n * C + c) * k2 + pq) * A + st];
                         float value;
-                        if (cx->tau_5D == ORC_HAAR) {
+                        if (cx->tau_5D == ORC_HAAR || cx->tau_5D == ORC_DCT) {
                             value = (*e) * (*e);
                             value /= (value + sg * sg);
                             *e = (*g) * value;
@@ -1051,7 +1066,12 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
         float *X = step == 1 ? G : E;
         for (unsigned c = 0; c < C; c++)
             for (unsigned st = 0; st < A; st++) {
-                if (nSx > 1) {
+                if (cx->tau_5D == ORC_DCT) {      /* core:2578-2593: coef_norm_inv_5d, REDFT01, 0.5 / sqrt(2 nSx) */
+                    for (unsigned n = 0; n < nSx; n++) vo[n] = X[((size_t) (n * C + c) * k2 + pq) * A + st] * cni5[n];
+                    r2r_1d(vo, ve, (int) nSx, 3);
+                    const float coef5 = 0.5f * (float) (SQRT2_INV_D) / sqrtf((float) nSx);
+                    for (unsigned n = 0; n < nSx; n++) X[((size_t) (n * C + c) * k2 + pq) * A + st] = ve[n] * coef5;
+                } else if (nSx > 1) {
                     for (unsigned n = 0; n < nSx; n++) vo[n] = X[((size_t) (n * C + c) * k2 + pq) * A + st];
                     if (cx->tau_5D == ORC_HAAR) orc_haar_inverse(vo, nSx);
                     else {
@@ -1066,6 +1086,23 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
         const float sg = cx->sigma_table[c];
         go->w[c] = wt[c] > 0.0f ? (sg > 0.0 ? 1.0f / (float) (sg * sg * wt[c]) : 1.0f / (float) (wt[c])) : 1.0f;
     }
+    if (g_use_sd) {      /* sd_weighting_5d, core:3140-3173 (N without the k^2 factor, as written there); bm3d.cpp:1345-1372 reads channel 0 for every c */
+        const float *X = step == 1 ? G : E;
+        const unsigned Nn = g_bm3d ? nSx * k2 : nSx * A;
+        for (unsigned c = 0; c < C; c++) {
+            const unsigned cc = g_bm3d ? 0 : c;
+            float mean = 0.0f, std = 0.0f;
+            for (unsigned pq = 0; pq < k2; pq++)
+                for (unsigned st = 0; st < A; st++)
+                    for (unsigned n = 0; n < nSx; n++) {
+                        const float x = X[((size_t) (n * C + cc) * k2 + pq) * A + st];
+                        mean += x;
+                        std += x * x;
+                    }
+            const float res = (std - mean * mean / (float) Nn) / (float) (Nn - 1);
+            go->w[c] = res > 0.0f ? 1.0f / sqrtf(res) : 0.0f;
+        }
+    }
     /* inverse angular + inverse spatial transforms; output Z[st][c][n][pq] */
     float *X = step == 1 ? G : E;
     for (unsigned n = 0; n < nSx; n++)
@@ -1078,6 +1115,8 @@ static void process_group(const pass_ctx *cx, int step, const float *noisy, cons
             }
         }
 }
+
+void orc_set_use_sd(int on) { g_use_sd = on; }
 
 int orc_pass(int step, float sigma, float lambda, const float *noisy_sym, const float *basic_sym, float *num_sym, float *den_sym,
              const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned pst, unsigned asw, unsigned w_b, unsigned h_b,
@@ -1113,7 +1152,7 @@ int orc_pass_ex(int step, float sigma, float lambda, const float *noisy_sym, con
     if (asw > MAXASW || chnls > 3 || k2 > 1024 || N > 64) return 1;
     if (tau_2D != ORC_ID && tau_2D != ORC_DCT && tau_2D != ORC_BIOR) return 1;
     if (tau_4D != ORC_ID && tau_4D != ORC_DCT && tau_4D != ORC_SADCT) return 1;
-    if (tau_5D != ORC_HAAR && tau_5D != ORC_HADAMARD) return 1;   /* 5-D DCT: out of scope this round */
+    if (tau_5D != ORC_HAAR && tau_5D != ORC_HADAMARD && tau_5D != ORC_DCT) return 1;
 
     pass_ctx *cx = (pass_ctx *) calloc(1, sizeof(pass_ctx));
     cx->asw = asw; cx->A = A; cx->chnls = chnls; cx->k = k; cx->k2 = k2; cx->N = N;
