@@ -31,6 +31,11 @@ struct LfTables {
     float sigma[3], sigma2[3];
     float thr[3][8];                     // hard threshold per channel and log2(nSx)
     float hadcoef[8];                    // 1 / nSx
+    // 5-D DCT along the similar patches (core:2524-2700, :2943-3130): REDFT10 / REDFT01 tables of length 2^lg packed one after
+    // the other (offset (4^lg - 1) / 3), preProcess_5d normalisers (core:3262-3276) and the hard threshold lambda sigma 2 sqrt2
+    float dct5f[1365], dct5i[1365];
+    float cn5_0[6], cn5_c[6], coef5inv[6];
+    float thr_dct[3];
 };
 
 __constant__ LfTables c_tab;

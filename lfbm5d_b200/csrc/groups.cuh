@@ -20,6 +20,7 @@ struct GroupArgs {
     const unsigned short *gmask;                  // [R] bit st = SAI st takes part in the group's angular shape (k_group_masks)
     const struct GroupShape *shape_lut;           // [2^A] SA-DCT index tables per shape (host-built, core:300-330)
     const unsigned char *act;                     // partial-window branch: [R] 1 = reference patch still to be processed; nullptr = all
+    int use_sd;                                   // 1: weight = 1 / sample std of the filtered group (core:3140-3173); 2: BM3D's variant (bm3d.cpp:1345)
     int partial;                                  // pst != cst: local 2-D variants (no zero column, core:1735)
     unsigned *ent;                                // [A][R*N] (y << 16 | x) of every patch that is aggregated, else LF_NOENT
     int R;
@@ -96,6 +97,56 @@ __device__ __forceinline__ float lf_block_sum_f(float v, float *sh)
     const int nw = (blockDim.x + 31) >> 5;
     for (int i = 0; i < nw; ++i) r += sh[i];
     return r;
+}
+
+// 1-D DCT of length ns = 2^lg along the similar patches with the normalisers of preProcess_5d (core:2544-2556, :2578-2593).
+// A rarely used option: kept out of line with rolled loops (compile time and register pressure of the common paths).
+__device__ __noinline__ void lf_dct5(float *v, int ns, int lg, bool fwd)
+{
+    const float *T = (fwd ? c_tab.dct5f : c_tab.dct5i) + ((1 << (2 * lg)) - 1) / 3;
+    float a[LF_MAXN], o[LF_MAXN];
+#pragma unroll 1
+    for (int n = 0; n < ns; ++n) a[n] = fwd ? v[n] : v[n] * (n == 0 ? LF_SQRT2_F : 1.0f);
+#pragma unroll 1
+    for (int kk = 0; kk < ns; ++kk) {
+        float acc = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < ns; ++j) acc = fmaf(a[j], T[kk * ns + j], acc);
+        o[kk] = acc;
+    }
+#pragma unroll 1
+    for (int n = 0; n < ns; ++n) v[n] = fwd ? o[n] * (n == 0 ? c_tab.cn5_0[lg] : c_tab.cn5_c[lg]) : o[n] * c_tab.coef5inv[lg];
+}
+
+// 5th-dimension filtering with the DCT (ht_filtering_dct_5d core:2524-2700, wiener_filtering_dct_5d :2943-3130) of one
+// (st, pq) vector; out of line like lf_dct5, its arrays live in local memory.
+__device__ __noinline__ float lf_filter5d_dct(int step, float *X, float *E, int base, int nstride, int ns, bool shrink, int c, int lg)
+{
+    float vo[LF_MAXN], ve[LF_MAXN];
+#pragma unroll 1
+    for (int n = 0; n < ns; ++n) { vo[n] = X[base + n * nstride]; if (step == 2) ve[n] = E[base + n * nstride]; }
+    lf_dct5(vo, ns, lg, true);
+    if (step == 2) lf_dct5(ve, ns, lg, true);
+    float wsum = 0.f;
+    if (shrink) {
+        const float T = c_tab.thr_dct[c], s2 = c_tab.sigma2[c];
+#pragma unroll 1
+        for (int n = 0; n < ns; ++n) {
+            if (step == 1) { if (fabsf(vo[n]) > T) wsum += 1.0f; else vo[n] = 0.0f; }
+            else {
+                float value = ve[n] * ve[n];
+                value = value / (value + s2);
+                ve[n] = vo[n] * value;
+                wsum += value;
+            }
+        }
+    }
+    float *out = step == 1 ? vo : ve;
+    lf_dct5(out, ns, lg, false);
+    float *dst = step == 1 ? X : E;
+#pragma unroll 1
+    for (int n = 0; n < ns; ++n) dst[base + n * nstride] = out[n];
+    return wsum;
 }
 
 // ---- 5th-dimension filtering of one (st, pq) vector; returns this thread's contribution to weight_table[c] ----
@@ -219,7 +270,7 @@ __device__ __forceinline__ void lf_r2r_small(const float *in, float *out, int n,
     }
 }
 // shape-adaptive variants (core:1969-2116, :2131-2264); rare path, generic code
-__device__ inline void lf_sadct_fwd(float *v, const GroupShape &sh, int asw)
+__device__ __noinline__ void lf_sadct_fwd(float *v, const GroupShape &sh, int asw)
 {
     float a[LF_MAXASW], b[LF_MAXASW];
     for (int s = 0; s < asw; ++s) {
@@ -243,7 +294,7 @@ __device__ inline void lf_sadct_fwd(float *v, const GroupShape &sh, int asw)
     const float coef = 0.5f * LF_SQRT2_INV_F;
     for (int st = 0; st < asw * asw; ++st) v[st] *= (float) sh.mask_dct[st] * coef;
 }
-__device__ inline void lf_sadct_inv(float *v, const GroupShape &sh, int asw)
+__device__ __noinline__ void lf_sadct_inv(float *v, const GroupShape &sh, int asw)
 {
     float a[LF_MAXASW], b[LF_MAXASW];
     const float c2 = 2.0f * LF_SQRT2_F;
@@ -494,6 +545,7 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     if (!lf_group_setup<false>(g, r, nSx, sh, sofs, szero)) return;
     const bool use_sadct = sh.use_sadct != 0 && g.tau_4D == 6;
     float *zdst = g.zbuf + (size_t) r * g.N * A * g.C * k2 + pq;
+    float sd_w = 0.f;
 
     for (int c = 0; c < g.C; ++c) {
         // ---- gather (core:286-299): raw patches ----
@@ -546,6 +598,7 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
             const int base = st * PS + poff;
             const bool shrink = !use_sadct || sh.mask_dct[st];
             const int ns = A * PS;
+            if (g.tau_5D == 5) { wpart += lf_filter5d_dct(STEP, X, E, base, ns, nSx, shrink, c, lg); continue; }
             switch (nSx) {
                 case 1:  wpart += lf_filter5d<STEP, 1>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
                 case 2:  wpart += lf_filter5d<STEP, 2>(X, E, base, ns, g.tau_5D, shrink, c, lg); break;
@@ -557,8 +610,20 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
         }
         const float wsum = lf_block_sum_f(wpart, red);     // also a barrier for the phase above
         const float sg = c_tab.sigma[c];
-        const float wgt = wsum > 0.0f ? (sg > 0.0f ? 1.0f / (c_tab.sigma2[c] * wsum) : 1.0f / wsum) : 1.0f;   // core:419-420
+        float wgt = wsum > 0.0f ? (sg > 0.0f ? 1.0f / (c_tab.sigma2[c] * wsum) : 1.0f / wsum) : 1.0f;   // core:419-420
         float *Z = STEP == 1 ? X : E;
+        if (g.use_sd) {      // sd_weighting_5d (core:3140-3173; N without the k^2 factor as written there); BM3D reads channel 0 for every c
+            if (g.use_sd == 1 || c == 0) {
+                float m1 = 0.f, m2 = 0.f;
+                for (int pa = sub; pa < npatch; pa += PPI) { const float xv = Z[pa * PS + poff]; m1 += xv; m2 += xv * xv; }
+                const float mean = lf_block_sum_f(m1, red);
+                const float sq = lf_block_sum_f(m2, red);
+                const float Nn = (float) (g.use_sd == 1 ? nSx * A : nSx * k2);
+                const float res = (sq - mean * mean / Nn) / (Nn - 1.0f);
+                sd_w = res > 0.0f ? 1.0f / sqrtf(res) : 0.0f;
+            }
+            wgt = sd_w;
+        }
         // ---- inverse angular transform (core:432-451) ----
         if (g.tau_4D != 4) {
             for (int n = sub; n < nSx; n += PPI) {

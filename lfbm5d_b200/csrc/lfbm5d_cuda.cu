@@ -105,6 +105,7 @@ struct PassCfg {
     int step;
     unsigned asw, A, C, W, H, n, nSim, nDisp, k, N, p, wb, hb;
     unsigned tau_2D, tau_4D, tau_5D;
+    unsigned useSD = 0;       // 0 none, 1 sd_weighting_5d, 2 BM3D's sd_weighting
     float tauMatch;
     std::vector<int> rows, cols;
 };
@@ -161,8 +162,7 @@ int validate(const lfbm5d_params *p, int step)
     if (p->p == 0) return fail("processing step must be >= 1");
     if (p->tau_2D != LFBM5D_ID && p->tau_2D != LFBM5D_DCT && p->tau_2D != LFBM5D_BIOR) return fail("tau_2D must be id, dct or bior");
     if (p->tau_4D != LFBM5D_ID && p->tau_4D != LFBM5D_DCT && p->tau_4D != LFBM5D_SADCT) return fail("tau_4D must be id, dct or sadct");
-    if (p->tau_5D != LFBM5D_HAAR && p->tau_5D != LFBM5D_HADAMARD) return fail("tau_5D must be haar or hw in this build (5-D dct: not yet)");
-    if (p->useSD) return fail("useSD weighting is not supported by this build");
+    if (p->tau_5D != LFBM5D_HAAR && p->tau_5D != LFBM5D_HADAMARD && p->tau_5D != LFBM5D_DCT) return fail("tau_5D must be haar, hw or dct");
     if (p->ang_major != LFBM5D_ROWMAJOR && p->ang_major != LFBM5D_COLMAJOR) return fail("ang_major must be row or col");
     if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");   // utilities.cpp:588-592
     if (p->height < p->k || p->width < p->k) return fail("image smaller than a patch");
@@ -232,6 +232,15 @@ int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau
                                 : lambda * T.sigma[c] * sqrtf((float) (1u << lg)) * (float) (SQRT2_D);
     }
     for (int lg = 0; lg < 8; lg++) T.hadcoef[lg] = 1.0f / (float) (1u << lg);
+    for (int lg = 0; lg < 6; lg++) {     // 5-D DCT: tables of length 2^lg and preProcess_5d (core:3262-3276)
+        const int n = 1 << lg, off = ((1 << (2 * lg)) - 1) / 3;
+        dct_tables(T.dct5f + off, T.dct5i + off, n);
+        const float coef = (float) (SQRT2_D) / sqrt((unsigned) n);
+        T.cn5_0[lg] = (float) (SQRT2_INV_D * coef);
+        T.cn5_c[lg] = coef;
+        T.coef5inv[lg] = 0.5f * (float) (SQRT2_INV_D) / sqrtf((float) n);
+    }
+    for (unsigned c = 0; c < p->chnls; c++) T.thr_dct[c] = lambda * T.sigma[c] * 2.0f * (float) (SQRT2_D);   // core:2566
     CK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -243,7 +252,7 @@ int make_passcfg(PassCfg &pc, int step, const lfbm5d_params *p, unsigned tau_4D)
     pc.asw = 2 * p->an + 1; pc.A = pc.asw * pc.asw; pc.C = p->chnls; pc.W = p->width; pc.H = p->height;
     pc.nSim = p->nSim; pc.nDisp = p->nDisp; pc.n = p->nSim + p->nDisp; pc.k = p->k; pc.N = p->N; pc.p = p->p;
     pc.wb = pc.W + 2 * pc.n; pc.hb = pc.H + 2 * pc.n;
-    pc.tau_2D = p->tau_2D; pc.tau_4D = tau_4D; pc.tau_5D = p->tau_5D;
+    pc.tau_2D = p->tau_2D; pc.tau_4D = tau_4D; pc.tau_5D = p->tau_5D; pc.useSD = p->useSD ? 1 : 0;
     float st[3];
     if (estimate_sigma(p->sigma, st, p->chnls, p->color_space)) return fail("unknown colour space");
     pc.tauMatch = (p->chnls == 1 ? 3.f : 1.f) * (st[0] < 35.0f ? (step == 1 ? 3000 : 2000) : 5000);   // core:146 / :915
@@ -522,7 +531,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     // ---- groups ----
     GroupArgs ga{};
     ga.gmask = ctx->gmask.as<unsigned short>(); ga.shape_lut = ctx->shape_lut.as<GroupShape>();
-    ga.act = partial ? ctx->act.as<unsigned char>() : nullptr; ga.partial = partial ? 1 : 0;
+    ga.act = partial ? ctx->act.as<unsigned char>() : nullptr; ga.partial = partial ? 1 : 0; ga.use_sd = (int) pc.useSD;
     ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
     ga.pst = pst; ga.nc = nc;
     // row padding removes the shared-memory bank conflicts of the 2-D passes (3 CTAs/SM without it measured slower)
@@ -540,18 +549,17 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
                                           : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8) {
+    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8 && pc.tau_5D != LFBM5D_DCT && !pc.useSD) {
         // register-resident path (no 2-D transform to stage); patches that contribute zeros read the zero block behind nsym
         CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
         if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
-        else if (pc.C == 1) k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
-        else k_groups_id16<0><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
+        else k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);       // validate(): C is 1 or 3
     }
-    else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR) {
+    else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR && !pc.useSD) {
         // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
         CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-        void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : (pc.C == 1 ? k_groups_w8<1> : k_groups_w8<0>);
+        void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : k_groups_w8<1>;       // validate(): C is 1 or 3
         const size_t smem8 = (size_t) 16 * 9 * W8_PS * 8;
         CK(cudaFuncSetAttribute((const void *) k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8));
         k8<<<R, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
@@ -571,11 +579,10 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
         aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
         aa.win = win;
         dim3 grid((pc.wb + 15) / 16, (pc.hb + 15) / 16, pc.A);
-        void (*kagg)(AggArgs) = k_aggregate<0, 0>;
+        void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
         if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
         else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
         else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
-        else if (pc.C == 1 && pc.k == 8) kagg = k_aggregate<8, 1>;
         LAUNCH(ctx, kagg, grid, 256, 0, aa);
     }
     CK(cudaGetLastError());
@@ -792,7 +799,6 @@ int validate_bm3d(const lfbm3d_params *p)
         if ((s ? p->pWien : p->pHard) == 0) return fail("processing step must be >= 1");
     }
     if (p->nHard + 1 < std::max(p->kHard, p->kWien)) return fail("nHard must be >= k - 1");
-    if (p->useSD_h || p->useSD_w) return fail("useSD weighting is not supported by this build");
     if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");
     if (p->width < 16 || p->height < 16) return fail("image smaller than a patch");
     return 0;
@@ -822,6 +828,7 @@ int bm3d_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy, const u
         q.color_space = p->color_space; q.nb_threads = 1;
         PassCfg pc;
         if (make_passcfg(pc, step, &q, LFBM5D_ID)) return 1;
+        pc.useSD = (step == 1 ? p->useSD_h : p->useSD_w) ? 2 : 0;
         float st3[3];
         if (estimate_sigma(p->sigma, st3, C, p->color_space)) return fail("unknown colour space");
         pc.tauMatch = step == 1 ? (C == 1 ? 3.f : 1.f) * (st3[0] < 35.0f ? 2500 : 5000)      // bm3d.cpp:340
