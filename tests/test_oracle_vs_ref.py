@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import golden_inputs as gi
 import lfdata
 
 pytestmark = pytest.mark.filterwarnings("ignore")
@@ -198,3 +199,64 @@ def test_lfbm3d_bit_exact(oracle, ref):
         rb, rd, rn = ref.run_bm3d_lf(noisy, mask, 10.0, 16, 16, 8, 8, 16, 32, 3, 3, t2h, t2w, 2.7)
         ob, od, on = oracle.run_bm3d_lf(noisy, mask, 10.0, 16, 16, 8, 8, 16, 32, 3, 3, t2h, t2w, 2.7)
         assert np.array_equal(rb, ob) and np.array_equal(rd, od) and np.array_equal(rn, on)
+
+
+def test_partial_window_branch_bit_exact(oracle, ref):
+    """`pst != cst` (core:531-821 / :1332-1658): single calls on accumulators with holes, and a complete grayscale run where
+    every window takes several core calls (LF_denoised_percent < 100 after the first SAI when C == 1)."""
+    _, _, sym = gi.pad_inputs(32, 40, 25.0)
+    z = np.zeros_like(sym)
+    mask, proc = np.ones(9, np.uint32), np.zeros(9, np.uint32)
+    num, den = oracle.run_pass(1, sym, None, z, z, mask, proc, 4, 3, 25.0, 2.7, 18, 6, 16, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    basic = np.where(den != 0, num / np.where(den != 0, den, 1), sym).astype(np.float32)
+    num, den = gi.partial_holes(num, den)
+    p2 = proc.copy(); p2[4] = 1
+    for pst in (1, 6, 3):
+        rn, rd = ref.pass_step1(sym, num, den, mask, p2, 4, pst, 3, 25.0, 2.7, 18, 6, 8, 4, 4, oracle.BIOR, oracle.DCT, oracle.HAAR)
+        on, od = oracle.run_pass(1, sym, None, num, den, mask, p2, pst, 3, 25.0, 2.7, 18, 6, 8, 4, 4, oracle.BIOR, oracle.DCT, oracle.HAAR, cst=4)
+        assert np.array_equal(rn, on) and np.array_equal(rd, od)
+        assert np.array_equal(rn, num) == (pst == 3)          # SAI 3 has no holes: nothing to do
+        rn, rd = ref.pass_step2(sym, basic, num, den, mask, p2, 4, pst, 3, 25.0, 18, 6, 8, 8, 4, oracle.DCT, oracle.SADCT, oracle.HAAR)
+        on, od = oracle.run_pass(2, sym, basic, num, den, mask, p2, pst, 3, 25.0, 0.0, 18, 6, 8, 8, 4, oracle.DCT, oracle.SADCT, oracle.HAAR, cst=4)
+        assert np.array_equal(rn, on) and np.array_equal(rd, od)
+    clean = np.ascontiguousarray(lfdata.synth_lf(3, 3, 24, 28)[:, :1])
+    noisy = oracle.add_noise(clean, 25.0)
+    m = np.ones(9, np.uint32)
+    m[4] = 0                                                      # empty centre SAI: already the first call is partial
+    rb, rn_ = ref.run_step1(noisy, m, 25.0, 2.7, 3, 3, 1, 8, 18, 6, 16, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    ob, on_, sched = oracle.run_step1(noisy, m, 25.0, 2.7, 3, 3, 1, 8, 18, 6, 16, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    assert int(sched[0][3]) > 1 and np.array_equal(rb, ob)
+
+
+def test_5d_dct_and_sd_weighting_bit_exact(oracle, ref):
+    """tau_5D = dct (core:2524-2700 / :2943-3130) and useSD (core:3140-3173; bm3d.cpp:1345-1372 incl. its channel-0 quirk)."""
+    _, _, sym = gi.pad_inputs(28, 32, 25.0)
+    z = np.zeros_like(sym)
+    mask, proc = np.ones(9, np.uint32), np.zeros(9, np.uint32)
+    num, den = oracle.run_pass(1, sym, None, z, z, mask, proc, 4, 3, 25.0, 2.7, 18, 6, 16, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    basic = np.where(den != 0, num / np.where(den != 0, den, 1), sym).astype(np.float32)
+    for (step, k, N, t2, t4, t5, sd) in [(1, 16, 8, oracle.ID, oracle.SADCT, oracle.DCT, 0), (2, 8, 16, oracle.DCT, oracle.SADCT, oracle.DCT, 0),
+                                         (1, 16, 8, oracle.ID, oracle.SADCT, oracle.HAAR, 1), (2, 8, 16, oracle.DCT, oracle.SADCT, oracle.HAAR, 1)]:
+        oracle.lib().orc_set_use_sd(sd)
+        try:
+            on, od = oracle.run_pass(step, sym, basic if step == 2 else None, z, z, mask, proc, 4, 3, 25.0, 2.7, 18, 6, k, N, 4, t2, t4, t5)
+        finally:
+            oracle.lib().orc_set_use_sd(0)
+        if step == 1:
+            rn, rd = ref.pass_step1(sym, z, z, mask, proc, 4, 4, 3, 25.0, 2.7, 18, 6, k, N, 4, t2, t4, t5, useSD=bool(sd))
+        else:
+            rn, rd = ref.pass_step2(sym, basic, z, z, mask, proc, 4, 4, 3, 25.0, 18, 6, k, N, 4, t2, t4, t5, useSD=bool(sd))
+        assert np.array_equal(rn, on) and np.array_equal(rd, od)
+    import ctypes as C
+    clean = lfdata.synth_lf(1, 1, 36, 40)
+    noisy = oracle.add_noise(clean, 20.0)
+    one = np.ones(1, np.uint32)
+    n = noisy.copy(); rb = np.zeros_like(n); rden = np.zeros_like(n)
+    assert ref.lib().ref_run_bm3d_LF(C.c_float(20.0), ref.fp(n), ref.up(ref.u32(one)), ref.fp(rb), ref.fp(rden), 1, 40, 36, 3, 16, 16, 8, 8, 16, 32, 3, 3,
+                                     1, 1, oracle.BIOR, oracle.DCT, C.c_float(2.7), oracle.OPP, 1) == 0
+    oracle.lib().orc_set_use_sd(1)
+    try:
+        ob, od, _ = oracle.run_bm3d_lf(noisy, one, 20.0, 16, 16, 8, 8, 16, 32, 3, 3, oracle.BIOR, oracle.DCT, 2.7)
+    finally:
+        oracle.lib().orc_set_use_sd(0)
+    assert np.array_equal(rb, ob) and np.array_equal(rden, od)
