@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
                 on[u] = (unsigned) dy < (unsigned) k && (unsigned) dx < (unsigned) k;
                 const int pq = dy * k + dx;
                 if (on[u]) {
-                    kv[u] = skaiser[pq];
+                    if (K != 16) kv[u] = skaiser[pq];      // the Kaiser window is all ones for k = 16 (bm3d.cpp:1144-1146): 1 * w == w
                     const float *zp = zb + ((size_t) e.y * (unsigned) k2 + (unsigned) pq);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) z[u][c] = c < C ? __ldg(zp + c * k2) : 0.f;
@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
                         if (c < C) {
-                            const float kw = kv[u] * wc[c];
+                            const float kw = K == 16 ? wc[c] : kv[u] * wc[c];
                             num[c] += kw * z[u][c];
                             den[c] += kw;
                         }
