@@ -284,17 +284,33 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     // per-warp staging of the 32 boundary pairs of a chunk (strip > 0): lane 0 reads one pair per step
     __shared__ unsigned long long s_bnd[SAT_NW][32];
     const unsigned sbn = (unsigned) __cvta_generic_to_shared(&s_bnd[warp][0]);
+    // Boundary pairs of the producer strip are fetched one chunk ahead: its progress flag is read (acquire) during chunk q-1,
+    // the 32 pairs of chunk q+1 are requested at the start of chunk q if that value already covers them, and only a late
+    // producer makes the warp spin. The loads land while the chunk computes instead of in front of it.
+    auto bnd_rows = [&](int q) { return min(lo + 32 * q + 32, g.row_end - 1); };
+    auto bnd_load = [&](int q) -> unsigned long long {
+        const int r = lo + 32 * q + 1 + lane;
+        return r < g.row_end ? lf_pk(__ldcg(&bnd_prev[r]), __ldcg(&bnd_prev[r + bB])) : 0ull;
+    };
+    // (not for the self variant with k = 16: at the 80-register cap of three CTAs per SM the extra state spills into its loop)
+    constexpr bool PREFETCH = !(SELF && K == 16);
+    unsigned long long nb2 = 0ull;
+    bool nb_have = false;
+    int prog_seen = (PREFETCH && hasplane && strip > 0) ? lf_ld_acquire(prog_prev) : 0;
     for (int q = 0; q < nchunks; ++q) {
         // stage the source rows of the next chunk while this one runs
         load_rows(lo + 32 * (q + 1) + k, lo + 32 * (q + 1) + 32 + k - 1);
         if (hasplane) {
             const int send = min(32 * q + 32, nsteps);
             if (strip > 0) {
-                const int rlast = min(lo + 32 * q + 32, g.row_end - 1);
-                wait_prev(rlast);
-                const int r = lo + 32 * q + 1 + lane;
-                s_bnd[warp][lane] = r < g.row_end ? lf_pk(__ldcg(&bnd_prev[r]), __ldcg(&bnd_prev[r + bB])) : 0ull;
+                if (!nb_have) { wait_prev(bnd_rows(q)); nb2 = bnd_load(q); }
+                s_bnd[warp][lane] = nb2;
                 __syncwarp();
+                nb_have = false;
+                if (PREFETCH && q + 1 < nchunks) {
+                    if (prog_seen >= bnd_rows(q + 1) + 1) { nb2 = bnd_load(q + 1); nb_have = true; }
+                    prog_seen = lf_ld_acquire(prog_prev);
+                }
                 unsigned bo = sbn;
 #pragma unroll (K == 8 ? 2 : 1)
                 for (int s = 32 * q + 1; s <= send; ++s, bo += 8) {
