@@ -115,7 +115,8 @@ struct PassCfg {
 struct lfbm5d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: early device->host copies of the host entry points
-    cudaEvent_t ev_rt = nullptr;
+    cudaStream_t stream3 = nullptr;                       // disparity matching of a pass, beside the self matching on `stream`
+    cudaEvent_t ev_rt = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_satb = nullptr;
     int num_sms = 148;
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
@@ -136,6 +137,11 @@ namespace {
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                          \
     do {                                                                    \
         kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);      \
+        (ctx)->stats.kernel_launches++;                                     \
+    } while (0)
+#define LAUNCH_ON(ctx, strm, kern, grid, block, smem, ...)                 \
+    do {                                                                    \
+        kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);             \
         (ctx)->stats.kernel_launches++;                                     \
     } while (0)
 
@@ -442,6 +448,26 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) std::max(self_strips, st_strips)) * 4, ctx->stream));
     cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
     if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
+    // Self matching (summed-area planes, selection) stays on the main stream; disparity matching (planes, argmin, ties) runs
+    // beside it on a second stream: the issue-bound plane kernels overlap with the bandwidth-bound argmin and the latency-bound
+    // selection / tie kernels of the other branch. The two launches use disjoint plane indices of bnd / progress.
+    cudaStream_t sB = ctx->stream3;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(sB, ctx->ev_fork, 0));
+    // the disparity planes are launched first: they finish first and their argmin then runs under the self planes
+    if (slot > 0) {
+        SatGeom g{};
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
+        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
+        g.gp = 1; g.negzero2 = 0x8000000080000000ull;
+        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
+        const int ngroups = (int) groups.size() - nself_groups;
+        auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
+        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        kfn<<<ngroups * st_strips, SAT_NW * 32, smem, sB>>>(g, ctx->satgroups.as<SatGroup>() + nself_groups,
+                                                            ctx->satplanes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
+        ctx->stats.kernel_launches++;
+    }
     if (nself > 0) {
         LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
         SatGeom g{};
@@ -459,21 +485,8 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
                                                                             nself_groups, ctx->bnd.as<float>(), flags, ticket);
         ctx->stats.kernel_launches++;
     }
-    if (slot > 0) {
-        SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
-        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
-        g.gp = 1; g.negzero2 = 0x8000000080000000ull;
-        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
-        const int ngroups = (int) groups.size() - nself_groups;
-        auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
-        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kfn<<<ngroups * st_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>() + nself_groups,
-                                                                     ctx->satplanes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
-        ctx->stats.kernel_launches++;
-    }
     (void) nself_planes;
-    if (ctx->timing) CK(cudaEventRecord(sat1, ctx->stream));
+    if (ctx->timing) { CK(cudaEventRecord(sat1, ctx->stream)); CK(cudaEventRecord(ctx->ev_satb, sB)); }
     // ---- selection ----
     if (nself > 0) {
         SelGeom sg{};
@@ -509,20 +522,22 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
         if (ctx->stielist.ensure(((size_t) slot * st_stride + 1) * 8)) return 1;
         uint2 *sl = ctx->stielist.as<uint2>();
         unsigned *sc = reinterpret_cast<unsigned *>(sl + (size_t) slot * st_stride);
-        CK(cudaMemsetAsync(sc, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(sc, 0, 4, sB));
         TieGeom tg{};
         tg.plane_stride = st_stride; tg.w = (int) pc.wb; tg.nDisp = (int) pc.nDisp; tg.lo = st_lo; tg.nstrips = st_strips; tg.SR = st_SR;
         tg.plane = (unsigned) plane;
         for (int s = 0; s < slot; s++) {
             const int st = stereo_sai[s];
             tg.sai[s] = st;
-            LAUNCH(ctx, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
+            LAUNCH_ON(ctx, sB, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
                    (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
                    ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned) s, sl, sc);
         }
-        LAUNCH(ctx, k_stereo_ties, ctx->num_sms * 8, 64, 0, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
-               ctx->first.as<unsigned>());
+        LAUNCH_ON(ctx, sB, k_stereo_ties, ctx->num_sms * 8, 64, 0, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
+                  ctx->first.as<unsigned>());
     }
+    CK(cudaEventRecord(ctx->ev_join, sB));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure(R * 2)) return 1;
     LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) R, (int) pc.wb, (unsigned) plane,
            (int) pc.A, (int) pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
@@ -596,6 +611,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
         cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[4]);
         cudaEventElapsedTime(&c, sat0, sat1);
+        { float cb = 0.f; cudaEventElapsedTime(&cb, sat0, ctx->ev_satb); c = std::max(c, cb); }      // both plane kernels done
         cudaEventElapsedTime(&d, ctx->ev[4], e2);
         ctx->stats.ms_block_matching += a; ctx->stats.ms_groups += b; ctx->stats.ms_sat += c; ctx->stats.ms_aggregate += d;
         cudaEventDestroy(e2);
@@ -915,6 +931,10 @@ int lfbm5d_create(lfbm5d_ctx **out, int device)
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_rt, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreate(&ctx->ev_satb));
     for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
     *out = ctx;
     return 0;
@@ -934,6 +954,10 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_rt) cudaEventDestroy(ctx->ev_rt);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_satb) cudaEventDestroy(ctx->ev_satb);
     delete ctx;
 }
 
