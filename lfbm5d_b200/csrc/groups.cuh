@@ -6,7 +6,6 @@
 
 struct GroupArgs {
     int C, asw, A, k, log2k, N, w, h, pst, nc;
-    int r0;                           // first reference patch of this launch (the pass is launched in bands of reference rows)
     int RS, PS;                       // shared-memory row stride / patch stride (floats)
     unsigned tau_2D, tau_4D, tau_5D;
     const int *rows, *cols;
@@ -529,7 +528,7 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     __shared__ unsigned char szero[LF_MAXN * LF_MAXA];    // patch reads as zeros (empty SAI, or column w-k: core:1697)
     constexpr int A = ASW * ASW;
     const int tid = threadIdx.x;
-    const int r = blockIdx.x + g.r0;
+    const int r = blockIdx.x;
     const int k = g.k, k2 = k * k, w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int nSx = (int) g.bm_count[r];
@@ -805,7 +804,7 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g, unsigned long 
     __shared__ __align__(16) unsigned sofs[8 * 9];
     constexpr int A = 9, k = 16, k2 = 256;
     const int tid = threadIdx.x;
-    const int r = blockIdx.x + g.r0;
+    const int r = blockIdx.x;
     const int w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int nSx = (int) g.bm_count[r];
@@ -838,7 +837,6 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g, unsigned long 
 // ------------------------------------------------------------------------------------------------------------
 struct AggArgs {
     int C, A, k, N, log2N, w, h, nc;
-    int ty0;                       // first tile row of this launch
     int R;
     const unsigned *ent;           // [A][R*N] (y << 16 | x) of the patches to add, LF_NOENT for the others (lf_group_setup)
     const float *zbuf, *wbuf;
@@ -861,8 +859,7 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
     if (!g.win.mask[st] || g.win.proc[st]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = K ? K : g.k, k2 = k * k, A = g.A, C = CC ? CC : g.C, N = g.N;
-    const int tyi = blockIdx.y + g.ty0;
-    const int y0 = tyi * 16, x0 = blockIdx.x * 16;
+    const int y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
     // a warp owns an 8 (x) by 4 (y) block of the tile: the squarer the footprint, the fewer patches touch it and the more
     // of its lanes each of them covers
     const int wy0 = y0 + (warp >> 1) * 4, wx0 = x0 + (warp & 1) * 8;
@@ -870,7 +867,7 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
     const bool inimg = y < g.h && x < g.w;
     const size_t plane = (size_t) g.w * g.h;
     for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
-    const int a_lo = g.arange[2 * tyi], a_hi = g.arange[2 * tyi + 1];
+    const int a_lo = g.arange[2 * blockIdx.y], a_hi = g.arange[2 * blockIdx.y + 1];
     const int b_lo = g.brange[2 * blockIdx.x], b_hi = g.brange[2 * blockIdx.x + 1];
     const int nbn = (b_hi - b_lo + 1) * N;                 // candidates per reference row: (column, n)
     float num[3] = { 0.f, 0.f, 0.f }, den[3] = { 0.f, 0.f, 0.f };

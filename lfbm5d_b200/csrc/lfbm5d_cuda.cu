@@ -112,15 +112,11 @@ struct PassCfg {
 
 } // namespace
 
-#define LF_NBANDS 6     // bands of reference rows per pass: aggregation of a band runs beside the group kernels of the next
-
 struct lfbm5d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: early device->host copies of the host entry points
     cudaStream_t stream3 = nullptr;                       // disparity matching of a pass, beside the self matching on `stream`
     cudaEvent_t ev_rt = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_satb = nullptr;
-    cudaEvent_t ev_band[LF_NBANDS] = {};                 // group kernels of a band of reference rows done
-    std::vector<int> arange_host;                         // per tile row: first / last candidate reference row (upload_grid)
     int num_sms = 148;
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
@@ -298,7 +294,6 @@ int upload_grid(lfbm5d_ctx *ctx, const PassCfg &pc)
         return rg;
     };
     const std::vector<int> ar = ranges(pc.rows, pc.hb), br = ranges(pc.cols, pc.wb);
-    ctx->arange_host = ar;
     if (ctx->arange.ensure(ar.size() * 4) || ctx->brange.ensure(br.size() * 4)) return 1;
     CK(cudaMemcpyAsync(ctx->arange.p, ar.data(), ar.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->brange.p, br.data(), br.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -569,71 +564,41 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
                                           : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const bool use_id16 = pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8 && pc.tau_5D != LFBM5D_DCT && !pc.useSD;
-    const bool use_w8 = pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR && !pc.useSD;
-    // patches that contribute zeros read the zero block behind nsym / bsym (register-resident and packed paths)
-    if (use_id16 || use_w8) CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-    if (use_w8) CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-    void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : k_groups_w8<1>;       // validate(): C is 1 or 3
-    const size_t smem8 = (size_t) 16 * 9 * W8_PS * 8;
-    if (use_w8) CK(cudaFuncSetAttribute((const void *) k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8));
-    auto launch_groups = [&](int r0, int count) {
-        ga.r0 = r0;
-        if (use_id16) {       // register-resident path (no 2-D transform to stage)
-            if (pc.C == 3) k_groups_id16<3><<<count, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
-            else k_groups_id16<1><<<count, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
-        } else if (use_w8)    // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
-            k8<<<count, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
-        else
-            kfn<<<count, 256, smem, ctx->stream>>>(ga);
-        ctx->stats.kernel_launches++;
-    };
-    AggArgs aa{};
-    aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
-    while ((1u << aa.log2N) < pc.N) aa.log2N++;
-    aa.w = pc.wb; aa.h = pc.hb; aa.nc = nc;
-    aa.R = (int) R; aa.ent = ctx->spos.as<unsigned>();
-    aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
-    aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
-    aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
-    aa.win = win;
-    void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
-    if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
-    else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
-    else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
-    const int ntx = ((int) pc.wb + 15) / 16, nty = ((int) pc.hb + 15) / 16;
-    auto launch_aggregate = [&](cudaStream_t strm, int ty0, int ty1) {      // tile rows [ty0, ty1)
-        if (ty1 <= ty0) return;
-        aa.ty0 = ty0;
-        kagg<<<dim3(ntx, ty1 - ty0, pc.A), 256, 0, strm>>>(aa);
-        ctx->stats.kernel_launches++;
-    };
-    // The pass is cut into bands of reference rows: the ordered aggregation of the tile rows whose candidate reference rows are
-    // all done runs on the second stream beside the group kernels of the next band (the group kernels are issue / FP32 bound,
-    // the aggregation streams zbuf). Every tile still adds its patches in the reference's order: the results do not change.
-    // With per-phase timing on, the two kernels run one after the other so that their times can be told apart.
-    static const int env_bands = getenv("LFBM5D_NBANDS") ? atoi(getenv("LFBM5D_NBANDS")) : LF_NBANDS;      // tuning aid
-    const int want = std::max(1, std::min(env_bands, LF_NBANDS));
-    const int nbands = (ctx->timing || nr < 4 * want || (int) ctx->arange_host.size() < 2 * nty) ? 1 : want;
-    if (nbands == 1) {
-        launch_groups(0, R);
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-        launch_aggregate(ctx->stream, 0, nty);
-    } else {
-        cudaStream_t sB = ctx->stream3;
-        int ty_done = 0;
-        for (int b = 0; b < nbands; b++) {
-            const int ra = (int) ((long long) nr * b / nbands), rb = (int) ((long long) nr * (b + 1) / nbands);
-            launch_groups(ra * nc, (rb - ra) * nc);
-            CK(cudaEventRecord(ctx->ev_band[b], ctx->stream));
-            int ty1 = ty_done;
-            while (ty1 < nty && (b == nbands - 1 || ctx->arange_host[2 * ty1 + 1] < rb)) ty1++;
-            CK(cudaStreamWaitEvent(sB, ctx->ev_band[b], 0));
-            launch_aggregate(sB, ty_done, ty1);
-            ty_done = ty1;
-        }
-        CK(cudaEventRecord(ctx->ev_join, sB));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8 && pc.tau_5D != LFBM5D_DCT && !pc.useSD) {
+        // register-resident path (no 2-D transform to stage); patches that contribute zeros read the zero block behind nsym
+        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
+        else k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);       // validate(): C is 1 or 3
+    }
+    else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR && !pc.useSD) {
+        // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
+        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+        void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : k_groups_w8<1>;       // validate(): C is 1 or 3
+        const size_t smem8 = (size_t) 16 * 9 * W8_PS * 8;
+        CK(cudaFuncSetAttribute((const void *) k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8));
+        k8<<<R, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
+    }
+    else
+        kfn<<<R, 256, smem, ctx->stream>>>(ga);
+    ctx->stats.kernel_launches++;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    {   // ordered aggregation of the staged patches
+        AggArgs aa{};
+        aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
+        while ((1u << aa.log2N) < pc.N) aa.log2N++;
+        aa.w = pc.wb; aa.h = pc.hb; aa.nc = nc;
+        aa.R = (int) R; aa.ent = ctx->spos.as<unsigned>();
+        aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
+        aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
+        aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
+        aa.win = win;
+        dim3 grid((pc.wb + 15) / 16, (pc.hb + 15) / 16, pc.A);
+        void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
+        if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
+        else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
+        else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
+        LAUNCH(ctx, kagg, grid, 256, 0, aa);
     }
     CK(cudaGetLastError());
     ctx->stats.window_passes++;
@@ -970,7 +935,6 @@ int lfbm5d_create(lfbm5d_ctx **out, int device)
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev_satb));
-    for (auto &ev : ctx->ev_band) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto &ev : ctx->ev) CK(cudaEventCreate(&ev));
     *out = ctx;
     return 0;
@@ -994,7 +958,6 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_satb) cudaEventDestroy(ctx->ev_satb);
-    for (auto &ev : ctx->ev_band) if (ev) cudaEventDestroy(ev);
     delete ctx;
 }
 
