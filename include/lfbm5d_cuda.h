@@ -108,11 +108,6 @@ int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const f
 int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
                          float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned cst,
                          unsigned pst, unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
-/* Block matching alone on one padded channel-0 plane (host pointers). */
-int lfbm5d_debug_bm_self(lfbm5d_ctx *ctx, const float *img, unsigned w_b, unsigned h_b, unsigned k, unsigned N, unsigned nHW,
-                         unsigned nSim, unsigned p, float tauMatch, unsigned *out_count, unsigned *out_idx);
-int lfbm5d_debug_bm_stereo(lfbm5d_ctx *ctx, const float *img1, const float *img2, unsigned w_b, unsigned h_b, unsigned k,
-                           unsigned nHW, unsigned nDisp, float tauMatch, unsigned *out_first, unsigned *out_shape);
 /* Window schedule of the last step call: (processed st, min_s, min_t, core calls) per window pass. */
 unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries);
 

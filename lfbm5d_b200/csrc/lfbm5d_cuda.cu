@@ -1105,19 +1105,4 @@ int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, cons
     return 0;
 }
 
-int lfbm5d_debug_bm_self(lfbm5d_ctx *ctx, const float *img, unsigned w_b, unsigned h_b, unsigned k, unsigned N, unsigned nHW,
-                         unsigned nSim, unsigned p, float tauMatch, unsigned *out_count, unsigned *out_idx)
-{
-    (void) ctx; (void) img; (void) w_b; (void) h_b; (void) k; (void) N; (void) nHW; (void) nSim; (void) p; (void) tauMatch;
-    (void) out_count; (void) out_idx;
-    return fail("use lfbm5d_debug_pass (it exports the match lists)");
-}
-int lfbm5d_debug_bm_stereo(lfbm5d_ctx *ctx, const float *img1, const float *img2, unsigned w_b, unsigned h_b, unsigned k,
-                           unsigned nHW, unsigned nDisp, float tauMatch, unsigned *out_first, unsigned *out_shape)
-{
-    (void) ctx; (void) img1; (void) img2; (void) w_b; (void) h_b; (void) k; (void) nHW; (void) nDisp; (void) tauMatch;
-    (void) out_first; (void) out_shape;
-    return fail("use lfbm5d_debug_pass (it exports the disparity matches)");
-}
-
 } // extern "C"
