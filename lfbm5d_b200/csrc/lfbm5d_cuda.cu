@@ -112,7 +112,23 @@ struct PassCfg {
 
 } // namespace
 
+// state of a step between step_begin and step_end
+struct StepState {
+    bool active = false;
+    int step = 0;
+    lfbm5d_params p{};
+    float *d_noisy = nullptr, *d_basic = nullptr;
+    std::vector<unsigned> mask, proc;
+    std::vector<char> touched;
+    unsigned remaining = 0, max_proc = 0, tau_4D = 0, tables_tau4 = 0, passes = 0;
+    PassCfg pc;
+    bool docolor = false;
+    cudaEvent_t e_begin = nullptr;
+    float bm0 = 0.f, gr0 = 0.f;
+};
+
 struct lfbm5d_ctx {
+    StepState ss;
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: early device->host copies of the host entry points
     cudaStream_t stream3 = nullptr;                       // disparity matching of a pass, beside the self matching on `stream`
@@ -619,31 +635,46 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     return 0;
 }
 
-// The reference's step driver for nb_threads == 1 (bm5d.cpp:165-407 / :861-1106) on device-resident light fields.
-int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy, float *d_basic, float *d_out, const unsigned *mask)
+// ---- the reference's step driver for nb_threads == 1 (bm5d.cpp:165-407 / :861-1106) on device-resident light fields, in three parts:
+// step_begin (colour transform, zeroed accumulators, tables), step_window (one angular window: pad, core call(s), unpad) and
+// step_end (num / den, inverse colour transforms). step_device strings them together with the reference's window selection;
+// the multi-GPU driver (lfbm5d_b200/dist.py) runs windows that share no SAI on different GPUs.
+int step_begin(lfbm5d_ctx *ctx, int step_, const lfbm5d_params *p_, float *d_noisy_, float *d_basic_, const unsigned *mask_)
 {
-    if (validate(p, step)) return 1;
+    if (validate(p_, step_)) return 1;
     CK(cudaSetDevice(ctx->device));
+    StepState &S0 = ctx->ss;
+    S0.p = *p_; S0.step = step_; S0.d_noisy = d_noisy_; S0.d_basic = d_basic_;
+    S0.mask.assign(mask_, mask_ + (size_t) p_->awidth * p_->aheight);
+    S0.active = true;
+    const lfbm5d_params *p = &S0.p;
+    const int step = step_;
+    float *d_noisy = d_noisy_, *d_basic = d_basic_;
+    const std::vector<unsigned> &mask = S0.mask;
     const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
     const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
     const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
     const unsigned C = p->chnls, W = p->width, H = p->height;
     const size_t HW = (size_t) W * H, each = HW * C;
     ctx->sched.clear();
-    cudaEvent_t e_begin = nullptr, e_end = nullptr;
-    if (ctx->timing) { CK(cudaEventCreate(&e_begin)); CK(cudaEventCreate(&e_end)); CK(cudaEventRecord(e_begin, ctx->stream)); }
-    const float bm0 = ctx->stats.ms_block_matching, gr0 = ctx->stats.ms_groups;
+    S0.e_begin = nullptr;
+    if (ctx->timing) { CK(cudaEventCreate(&S0.e_begin)); CK(cudaEventRecord(S0.e_begin, ctx->stream)); }
+    S0.bm0 = ctx->stats.ms_block_matching; S0.gr0 = ctx->stats.ms_groups;
 
     // a window containing an empty SAI turns dct into sadct for the rest of the step (bm5d.cpp:276-280)
-    unsigned tau_4D = p->tau_4D;
-    std::vector<unsigned> proc(asize);
-    unsigned remaining = 0;
+    unsigned &tau_4D = S0.tau_4D;
+    tau_4D = p->tau_4D;
+    std::vector<unsigned> &proc = S0.proc;
+    proc.assign(asize, 0);
+    unsigned &remaining = S0.remaining;
+    remaining = 0;
     for (unsigned st = 0; st < asize; st++) { proc[st] = !mask[st]; remaining += proc[st] == 0; }
-    const unsigned max_proc = remaining;
+    S0.max_proc = remaining;
 
     if (ctx->mask.ensure(asize * 4) || ctx->num.ensure(asize * each * 4) || ctx->den.ensure(asize * each * 4)) return 1;
-    CK(cudaMemcpyAsync(ctx->mask.p, mask, asize * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->mask.p, mask.data(), asize * 4, cudaMemcpyHostToDevice, ctx->stream));
     const bool docolor = C == 3 && p->color_space != LFBM5D_RGB;
+    S0.docolor = docolor;
     if (docolor) {
         LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_noisy, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
         if (step == 2) LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_basic, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
@@ -651,141 +682,229 @@ int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_nois
     CK(cudaMemsetAsync(ctx->num.p, 0, asize * each * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
 
-    PassCfg pc;
+    PassCfg &pc = S0.pc;
+    pc = PassCfg();
     if (make_passcfg(pc, step, p, tau_4D)) return 1;
     if (setup_tables(ctx, step, p, tau_4D)) return 1;
     if (ensure_pass_buffers(ctx, pc) || upload_grid(ctx, pc)) return 1;
-    unsigned tables_tau4 = tau_4D;
+    S0.tables_tau4 = tau_4D;
+    S0.touched.assign(asize, 0);
+    S0.passes = 0;
+    return 0;
+}
 
-    std::vector<char> touched(asize, 0);
-    unsigned passes = 0;
+// bm5d.cpp:182-202: the centre SAI first, then the unprocessed SAI with the most zero weights (ties to the highest index)
+int step_select(lfbm5d_ctx *ctx, unsigned &ps, unsigned &pt)
+{
+    StepState &S = ctx->ss;
+    const lfbm5d_params *p = &S.p;
+    const int step = S.step;
+    float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
+    const std::vector<unsigned> &mask = S.mask;
+    std::vector<unsigned> &proc = S.proc;
+    std::vector<char> &touched = S.touched;
+    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
+    const unsigned max_proc = S.max_proc;
+    PassCfg &pc = S.pc;
+    const bool docolor = S.docolor;
+    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
+    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    const size_t HW = (size_t) W * H, each = HW * C;
     unsigned long long *counters = ctx->counters.as<unsigned long long>();
-    while (remaining) {
-        unsigned ps, pt, pst_g = 0;
-        if (remaining == max_proc && mask[cst]) { ps = cs; pt = ct; }
-        else {   // bm5d.cpp:189-202: most entries still at 0, ties to the highest index
-            long long best = -1;
-            std::vector<unsigned> need;
-            for (unsigned st = 0; st < asize; st++) if (!proc[st] && touched[st]) need.push_back(st);
-            std::vector<unsigned long long> zc(asize, (unsigned long long) each);
-            if (!need.empty()) {
-                if (ctx->counters.ensure((need.size() + 8) * 8)) return 1;
-                counters = ctx->counters.as<unsigned long long>();
-                CK(cudaMemsetAsync(counters, 0, need.size() * 8, ctx->stream));
-                for (size_t i = 0; i < need.size(); i++)
-                    LAUNCH(ctx, k_count_zero, grid_for(ctx, each), 256, 0, ctx->den.as<float>() + need[i] * each, each, counters + i);
-                std::vector<unsigned long long> h(need.size());
-                CK(cudaMemcpyAsync(h.data(), counters, need.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                for (size_t i = 0; i < need.size(); i++) zc[need[i]] = h[i];
-            }
-            for (unsigned st = 0; st < asize; st++) {
-                if (proc[st]) continue;
-                const long long z = (long long) (int) zc[st];     // the reference keeps the count in an int
-                if (z >= best) { pst_g = st; best = z; }
-            }
-            if (p->ang_major == LFBM5D_ROWMAJOR) { ps = pst_g / p->awidth; pt = pst_g - ps * p->awidth; }
-            else { pt = pst_g / p->aheight; ps = pst_g - pt * p->aheight; }
-        }
-        int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
-        angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
-        angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
-        const unsigned cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
-        LfWindow win{};
-        win.A = (int) Aw;
-        unsigned n_unproc = 0;
-        for (unsigned s_a = 0; s_a < asw; s_a++)
-            for (unsigned t_a = 0; t_a < asw; t_a++) {
-                const unsigned s = s_a + min_s, t = t_a + min_t;
-                unsigned st, a;
-                if (p->ang_major == LFBM5D_ROWMAJOR) { st = s * p->awidth + t; a = s_a * asw + t_a; }
-                else { st = s + t * p->aheight; a = s_a + t_a * asw; }
-                win.st[a] = (int) st;
-                win.mask[a] = mask[st];
-                win.proc[a] = !mask[st];
-                n_unproc += mask[st] != 0;
-            }
-        if (n_unproc != Aw && tau_4D == LFBM5D_DCT) tau_4D = LFBM5D_SADCT;
-        if (tau_4D != tables_tau4) {
-            pc.tau_4D = tau_4D;
-            if (setup_tables(ctx, step, p, tau_4D)) return 1;
-            tables_tau4 = tau_4D;
-        }
-        LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) Aw * pc.wb * pc.hb), 256, 0, d_noisy, step == 2 ? d_basic : (const float *) nullptr,
-               ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
-               ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
-        const unsigned max_unproc = n_unproc;
-        unsigned calls = 0;
-        while (n_unproc) {
-            unsigned pst_asw = 0;
-            if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
-            else {
-                // bm5d.cpp:318-333: the unprocessed SAI of the window with the most zero weights in its padded den (all channels),
-                // ties to the highest slot; the reference keeps the count in an int
-                const size_t each_b = (size_t) C * pc.wb * pc.hb;
-                if (ctx->counters.ensure((Aw + 8) * 8)) return 1;
-                counters = ctx->counters.as<unsigned long long>();
-                CK(cudaMemsetAsync(counters, 0, Aw * 8, ctx->stream));
-                for (unsigned a = 0; a < Aw; a++)
-                    if (win.proc[a] == 0)
-                        LAUNCH(ctx, k_count_zero, grid_for(ctx, each_b), 256, 0, ctx->densym.as<float>() + a * each_b, each_b, counters + a);
-                std::vector<unsigned long long> hz(Aw);
-                CK(cudaMemcpyAsync(hz.data(), counters, Aw * 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                long long best = -1;
-                for (unsigned a = 0; a < Aw; a++) {
-                    if (win.proc[a]) continue;
-                    const long long z = (long long) (int) hz[a];
-                    if (z >= best) { pst_asw = a; best = z; }
-                }
-            }
-            if (calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937)
-                LAUNCH(ctx, k_est0, grid_for(ctx, pc.A * (size_t) pc.wb * pc.hb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
-                       ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (size_t) pc.wb * pc.hb, (int) pc.C);
-            if (run_pass(ctx, pc, win, (int) pst_asw, (int) cst_asw)) return 1;
-            calls++;
-            win.proc[pst_asw] += 1;
-            proc[win.st[pst_asw]] += 1;
-            // LF_denoised_percent (utilities_LF.cpp:967-995): float counter (saturates at 2^24), normalised without C
-            CK(cudaMemsetAsync(counters, 0, 8, ctx->stream));
-            LAUNCH(ctx, k_count_denoised, grid_for(ctx, (size_t) Aw * C * (H - pc.k + 1) * (W - pc.k + 1)), 256, 0, ctx->densym.as<float>(),
-                   win, (int) W, (int) H, (int) C, (int) pc.n, (int) pc.k, counters);
-            unsigned long long cnt = 0;
-            CK(cudaMemcpyAsync(&cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
+    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
+    (void) H; (void) HW; (void) each; (void) counters;
+    unsigned pst_g = 0;
+    if (remaining == max_proc && mask[cst]) { ps = cs; pt = ct; }
+    else {   // bm5d.cpp:189-202: most entries still at 0, ties to the highest index
+        long long best = -1;
+        std::vector<unsigned> need;
+        for (unsigned st = 0; st < asize; st++) if (!proc[st] && touched[st]) need.push_back(st);
+        std::vector<unsigned long long> zc(asize, (unsigned long long) each);
+        if (!need.empty()) {
+            if (ctx->counters.ensure((need.size() + 8) * 8)) return 1;
+            counters = ctx->counters.as<unsigned long long>();
+            CK(cudaMemsetAsync(counters, 0, need.size() * 8, ctx->stream));
+            for (size_t i = 0; i < need.size(); i++)
+                LAUNCH(ctx, k_count_zero, grid_for(ctx, each), 256, 0, ctx->den.as<float>() + need[i] * each, each, counters + i);
+            std::vector<unsigned long long> h(need.size());
+            CK(cudaMemcpyAsync(h.data(), counters, need.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            const float fcnt = (float) std::min<unsigned long long>(cnt, 16777216ull);
-            unsigned nmask = 0;
-            for (unsigned a = 0; a < Aw; a++) nmask += win.mask[a] == 1;
-            const float pct = fcnt * 100.0f / (float) nmask / (float) (H - pc.k + 1) / (float) (W - pc.k + 1);
-            if (pct >= 100.0f)
-                for (unsigned a = 0; a < Aw; a++)
-                    if (win.proc[a] == 0) { win.proc[a] += 1; proc[win.st[a]] += 1; }
-            n_unproc = 0;
-            for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
+            for (size_t i = 0; i < need.size(); i++) zc[need[i]] = h[i];
         }
-        LAUNCH(ctx, k_unpad_window, grid_for(ctx, (size_t) Aw * each), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
-               ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
-        for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) touched[win.st[a]] = 1;
-        ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
-        ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
-        remaining = 0;
-        for (unsigned st = 0; st < asize; st++) remaining += proc[st] == 0;
-        passes++;
-        if (ctx->max_passes && passes >= ctx->max_passes) break;
+        for (unsigned st = 0; st < asize; st++) {
+            if (proc[st]) continue;
+            const long long z = (long long) (int) zc[st];     // the reference keeps the count in an int
+            if (z >= best) { pst_g = st; best = z; }
+        }
+        if (p->ang_major == LFBM5D_ROWMAJOR) { ps = pst_g / p->awidth; pt = pst_g - ps * p->awidth; }
+        else { pt = pst_g / p->aheight; ps = pst_g - pt * p->aheight; }
     }
+    return 0;
+}
+
+// One angular window centred (and clamped) on SAI (ps, pt): bm5d.cpp:204-402
+int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
+{
+    StepState &S = ctx->ss;
+    const lfbm5d_params *p = &S.p;
+    const int step = S.step;
+    float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
+    const std::vector<unsigned> &mask = S.mask;
+    std::vector<unsigned> &proc = S.proc;
+    std::vector<char> &touched = S.touched;
+    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
+    const unsigned max_proc = S.max_proc;
+    PassCfg &pc = S.pc;
+    const bool docolor = S.docolor;
+    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
+    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    const size_t HW = (size_t) W * H, each = HW * C;
+    unsigned long long *counters = ctx->counters.as<unsigned long long>();
+    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
+    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
+    (void) H; (void) HW; (void) each; (void) counters;
+    int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
+    angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
+    angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
+    const unsigned cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
+    LfWindow win{};
+    win.A = (int) Aw;
+    unsigned n_unproc = 0;
+    for (unsigned s_a = 0; s_a < asw; s_a++)
+        for (unsigned t_a = 0; t_a < asw; t_a++) {
+            const unsigned s = s_a + min_s, t = t_a + min_t;
+            unsigned st, a;
+            if (p->ang_major == LFBM5D_ROWMAJOR) { st = s * p->awidth + t; a = s_a * asw + t_a; }
+            else { st = s + t * p->aheight; a = s_a + t_a * asw; }
+            win.st[a] = (int) st;
+            win.mask[a] = mask[st];
+            win.proc[a] = !mask[st];
+            n_unproc += mask[st] != 0;
+        }
+    if (n_unproc != Aw && tau_4D == LFBM5D_DCT) tau_4D = LFBM5D_SADCT;
+    if (tau_4D != tables_tau4) {
+        pc.tau_4D = tau_4D;
+        if (setup_tables(ctx, step, p, tau_4D)) return 1;
+        tables_tau4 = tau_4D;
+    }
+    LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) Aw * pc.wb * pc.hb), 256, 0, d_noisy, step == 2 ? d_basic : (const float *) nullptr,
+           ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
+           ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
+    const unsigned max_unproc = n_unproc;
+    unsigned calls = 0;
+    while (n_unproc) {
+        unsigned pst_asw = 0;
+        if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
+        else {
+            // bm5d.cpp:318-333: the unprocessed SAI of the window with the most zero weights in its padded den (all channels),
+            // ties to the highest slot; the reference keeps the count in an int
+            const size_t each_b = (size_t) C * pc.wb * pc.hb;
+            if (ctx->counters.ensure((Aw + 8) * 8)) return 1;
+            counters = ctx->counters.as<unsigned long long>();
+            CK(cudaMemsetAsync(counters, 0, Aw * 8, ctx->stream));
+            for (unsigned a = 0; a < Aw; a++)
+                if (win.proc[a] == 0)
+                    LAUNCH(ctx, k_count_zero, grid_for(ctx, each_b), 256, 0, ctx->densym.as<float>() + a * each_b, each_b, counters + a);
+            std::vector<unsigned long long> hz(Aw);
+            CK(cudaMemcpyAsync(hz.data(), counters, Aw * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            long long best = -1;
+            for (unsigned a = 0; a < Aw; a++) {
+                if (win.proc[a]) continue;
+                const long long z = (long long) (int) hz[a];
+                if (z >= best) { pst_asw = a; best = z; }
+            }
+        }
+        if (calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937)
+            LAUNCH(ctx, k_est0, grid_for(ctx, pc.A * (size_t) pc.wb * pc.hb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
+                   ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (size_t) pc.wb * pc.hb, (int) pc.C);
+        if (run_pass(ctx, pc, win, (int) pst_asw, (int) cst_asw)) return 1;
+        calls++;
+        win.proc[pst_asw] += 1;
+        proc[win.st[pst_asw]] += 1;
+        // LF_denoised_percent (utilities_LF.cpp:967-995): float counter (saturates at 2^24), normalised without C
+        CK(cudaMemsetAsync(counters, 0, 8, ctx->stream));
+        LAUNCH(ctx, k_count_denoised, grid_for(ctx, (size_t) Aw * C * (H - pc.k + 1) * (W - pc.k + 1)), 256, 0, ctx->densym.as<float>(),
+               win, (int) W, (int) H, (int) C, (int) pc.n, (int) pc.k, counters);
+        unsigned long long cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const float fcnt = (float) std::min<unsigned long long>(cnt, 16777216ull);
+        unsigned nmask = 0;
+        for (unsigned a = 0; a < Aw; a++) nmask += win.mask[a] == 1;
+        const float pct = fcnt * 100.0f / (float) nmask / (float) (H - pc.k + 1) / (float) (W - pc.k + 1);
+        if (pct >= 100.0f)
+            for (unsigned a = 0; a < Aw; a++)
+                if (win.proc[a] == 0) { win.proc[a] += 1; proc[win.st[a]] += 1; }
+        n_unproc = 0;
+        for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
+    }
+    LAUNCH(ctx, k_unpad_window, grid_for(ctx, (size_t) Aw * each), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
+           ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
+    for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) touched[win.st[a]] = 1;
+    ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
+    ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
+    remaining = 0;
+    for (unsigned st = 0; st < asize; st++) remaining += proc[st] == 0;
+    passes++;
+    return 0;
+}
+
+int step_end(lfbm5d_ctx *ctx, float *d_out)
+{
+    StepState &S = ctx->ss;
+    const lfbm5d_params *p = &S.p;
+    const int step = S.step;
+    float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
+    const std::vector<unsigned> &mask = S.mask;
+    std::vector<unsigned> &proc = S.proc;
+    std::vector<char> &touched = S.touched;
+    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
+    const unsigned max_proc = S.max_proc;
+    PassCfg &pc = S.pc;
+    const bool docolor = S.docolor;
+    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
+    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    const size_t HW = (size_t) W * H, each = HW * C;
+    unsigned long long *counters = ctx->counters.as<unsigned long long>();
+    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
+    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
+    (void) H; (void) HW; (void) each; (void) counters;
     LAUNCH(ctx, k_final, grid_for(ctx, asize * HW), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), d_noisy, d_basic, d_out,
            ctx->mask.as<unsigned>(), asize, HW, (int) C, step, p->color_space, docolor ? 1 : 0);
     CK(cudaGetLastError());
     if (ctx->timing) {
+        cudaEvent_t e_end = nullptr;
+        CK(cudaEventCreate(&e_end));
         CK(cudaEventRecord(e_end, ctx->stream));
         CK(cudaEventSynchronize(e_end));
         float total = 0;
-        cudaEventElapsedTime(&total, e_begin, e_end);
-        ctx->stats.ms_other += total - (ctx->stats.ms_block_matching - bm0) - (ctx->stats.ms_groups - gr0);
-        cudaEventDestroy(e_begin); cudaEventDestroy(e_end);
+        cudaEventElapsedTime(&total, S.e_begin, e_end);
+        ctx->stats.ms_other += total - (ctx->stats.ms_block_matching - S.bm0) - (ctx->stats.ms_groups - S.gr0);
+        cudaEventDestroy(S.e_begin); cudaEventDestroy(e_end);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    S.active = false;
     return 0;
+}
+
+int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy, float *d_basic, float *d_out, const unsigned *mask)
+{
+    if (step_begin(ctx, step, p, d_noisy, d_basic, mask)) return 1;
+    ctx->sched.clear();
+    while (ctx->ss.remaining) {
+        unsigned ps = 0, pt = 0;
+        if (step_select(ctx, ps, pt) || step_window(ctx, ps, pt)) return 1;
+        if (ctx->max_passes && ctx->ss.passes >= ctx->max_passes) break;
+    }
+    return step_end(ctx, d_out);
 }
 
 // out[c][i][j] = numsym / densym on the unpadded interior, without a zero guard (bm3d.cpp:476-477, :682-683)
