@@ -94,6 +94,21 @@ int lfbm3d_run_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy_io
 /* stop after this many window passes per step (0 = run to completion); for bounded measurements only */
 void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned max_passes);
 
+/* ---- window-level entry points -------------------------------------------------------------------
+ * A step = lfbm5d_step_begin, one lfbm5d_step_window per angular window in the order of the reference's schedule
+ * (bm5d.cpp:171-402), lfbm5d_step_end; lfbm5d_step{1,2}_device do exactly that. The schedule is static (lfbm5d_step_plan) and
+ * windows that share no SAI commute, so a multi-GPU driver may run the windows of one plan level on different GPUs and copy the
+ * accumulators (num / den, [asize][chnls][height][width] floats) of their SAIs to the others before the next level
+ * (lfbm5d_b200/dist.py). Results are those of the sequential order. */
+int lfbm5d_step_begin(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io, const unsigned *sai_mask);
+int lfbm5d_step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt);                 /* window centred (clamped) on SAI (s, t) = (ps, pt) */
+int lfbm5d_step_end(lfbm5d_ctx *ctx, float *d_out);
+int lfbm5d_step_accumulators(lfbm5d_ctx *ctx, float **d_num, float **d_den, size_t *floats_per_sai);
+/* out[6 * i + ...] = (ps, pt, first s of the window, first t, level, sadct) of window i; returns the number of windows */
+unsigned lfbm5d_step_plan(const lfbm5d_params *p, const unsigned *sai_mask, unsigned *out, unsigned max_entries);
+/* a window with an empty SAI earlier in the sequential order turns tau_4D = dct into sadct for the rest of the step (bm5d.cpp:276-280) */
+int lfbm5d_step_force_sadct(lfbm5d_ctx *ctx);
+
 /* ---- parity/debug exports (used by tests only) ---------------------------------------------------
  * One window pass (the reference's bm5d_1st_step / bm5d_2nd_step, `pst == cst` branch) on HOST padded
  * buffers [A][chnls][h_b][w_b], A = (2*an+1)^2, h_b = height + 2*(nSim+nDisp); p->width/height are the

@@ -44,7 +44,8 @@ class Stats(C.Structure):
 EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset_stats", "lfbm5d_get_stats",
            "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
            "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_pass_ex",
-           "lfbm5d_debug_schedule"]
+           "lfbm5d_debug_schedule", "lfbm5d_step_begin", "lfbm5d_step_window", "lfbm5d_step_end", "lfbm5d_step_accumulators",
+           "lfbm5d_step_plan", "lfbm5d_step_force_sadct"]
 
 _lib = None
 
@@ -73,6 +74,16 @@ def make_params3d(sigma, asize, width, height, chnls, nHard, nWien, kHard, kWien
                   tau_2D_wien, lambdaHard3D=2.7, color_space=OPP, nb_threads=1):
     return Params3D(sigma, asize, width, height, chnls, nHard, nWien, kHard, kWien, NHard, NWien, pHard, pWien, 0, 0, tau_2D_hard,
                     tau_2D_wien, lambdaHard3D, color_space, nb_threads)
+
+
+def step_plan(prm, mask):
+    """Static window schedule of a step: rows (ps, pt, min_s, min_t, level, sadct); windows of one level share no SAI."""
+    lib = load_library()
+    m = np.ascontiguousarray(mask, np.uint32)
+    out = np.zeros((int(prm.awidth * prm.aheight) + 1, 6), np.uint32)
+    lib.lfbm5d_step_plan.restype = C.c_uint
+    n = lib.lfbm5d_step_plan(C.byref(prm), m.ctypes.data_as(C.POINTER(C.c_uint)), out.ctypes.data_as(C.POINTER(C.c_uint)), out.shape[0])
+    return out[:n]
 
 
 def _fp(a):
@@ -178,6 +189,30 @@ class LFBM5D(object):
         if self.lib.lfbm5d_step2_device(self.ctx, C.byref(prm), C.c_void_p(d_noisy), C.c_void_p(d_basic), _up(m),
                                         C.c_void_p(d_out)) != 0:
             raise RuntimeError("lfbm5d_step2_device: " + self.error())
+
+    # -- window-level entry points (see lfbm5d_b200/dist.py) -------------------------------------------
+    def step_begin(self, step, prm, d_noisy, d_basic, mask):
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_step_begin(self.ctx, int(step), C.byref(prm), C.c_void_p(d_noisy), C.c_void_p(d_basic or 0), _up(m)) != 0:
+            raise RuntimeError("lfbm5d_step_begin: " + self.error())
+
+    def step_window(self, ps, pt):
+        if self.lib.lfbm5d_step_window(self.ctx, int(ps), int(pt)) != 0:
+            raise RuntimeError("lfbm5d_step_window: " + self.error())
+
+    def step_end(self, d_out):
+        if self.lib.lfbm5d_step_end(self.ctx, C.c_void_p(d_out)) != 0:
+            raise RuntimeError("lfbm5d_step_end: " + self.error())
+
+    def step_force_sadct(self):
+        self.lib.lfbm5d_step_force_sadct(self.ctx)
+
+    def step_accumulators(self):
+        """(device pointer of num, device pointer of den, floats per SAI) of the step in progress."""
+        pn, pd, each = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        if self.lib.lfbm5d_step_accumulators(self.ctx, C.byref(pn), C.byref(pd), C.byref(each)) != 0:
+            raise RuntimeError("lfbm5d_step_accumulators: " + self.error())
+        return pn.value, pd.value, each.value
 
     # -- parity/debug: one window pass on padded host buffers --------------------------------------
     def debug_pass(self, step, prm, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, debug=False, cst=None):

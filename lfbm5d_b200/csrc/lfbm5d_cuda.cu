@@ -1153,6 +1153,98 @@ int lfbm3d_run_device(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *d_noisy_io
     return bm3d_device(ctx, p, d_noisy_io, sai_mask, d_basic_out, d_denoised_out);
 }
 
+// ---- window-level entry points (multi-GPU driver: windows that share no SAI run on different GPUs) ----
+int lfbm5d_step_begin(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io, const unsigned *sai_mask)
+{
+    if (!ctx || !p || !d_noisy_io || !sai_mask || (step == 2 && !d_basic_io)) return fail("null argument");
+    if (step != 1 && step != 2) return fail("step must be 1 or 2");
+    return step_begin(ctx, step, p, d_noisy_io, d_basic_io, sai_mask);
+}
+
+int lfbm5d_step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
+{
+    if (!ctx || !ctx->ss.active) return fail("no step in progress");
+    if (ps >= ctx->ss.p.aheight || pt >= ctx->ss.p.awidth) return fail("SAI index out of range");
+    return step_window(ctx, ps, pt);
+}
+
+int lfbm5d_step_end(lfbm5d_ctx *ctx, float *d_out)
+{
+    if (!ctx || !ctx->ss.active || !d_out) return fail("no step in progress");
+    return step_end(ctx, d_out);
+}
+
+int lfbm5d_step_accumulators(lfbm5d_ctx *ctx, float **d_num, float **d_den, size_t *floats_per_sai)
+{
+    if (!ctx || !ctx->ss.active || !d_num || !d_den) return fail("no step in progress");
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_num = ctx->num.as<float>();
+    *d_den = ctx->den.as<float>();
+    if (floats_per_sai) *floats_per_sai = (size_t) ctx->ss.p.width * ctx->ss.p.height * ctx->ss.p.chnls;
+    return 0;
+}
+
+unsigned lfbm5d_step_plan(const lfbm5d_params *p, const unsigned *sai_mask, unsigned *out, unsigned max_entries)
+{
+    // Static form of the reference's window selection (bm5d.cpp:182-202): every SAI of a finished window is marked processed
+    // (:370-382 or the end of the inner loop), so an unprocessed SAI has never been aggregated into, all of them tie on the
+    // number of zero weights and the `>=` scan keeps the highest index. Entries: (ps, pt, min_s, min_t, level, sadct) where
+    // level = longest chain of earlier windows sharing an SAI (same-level windows commute) and sadct = 1 once a window with
+    // an empty SAI has been seen in sequential order (:276-280 is sticky).
+    if (!p || !sai_mask || !out) return 0;
+    const unsigned aw = p->awidth, ah = p->aheight, asize = aw * ah, asw = 2 * p->an + 1;
+    if (asw > aw || asw > ah) return 0;
+    std::vector<unsigned> proc(asize);
+    unsigned remaining = 0;
+    for (unsigned st = 0; st < asize; st++) { proc[st] = !sai_mask[st]; remaining += proc[st] == 0; }
+    const unsigned max_proc = remaining;
+    const unsigned cs = ah / 2, ct = aw / 2;
+    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * aw + ct : cs + ct * ah;
+    std::vector<int> last_level(asize, -1);
+    unsigned n = 0, sticky = 0;
+    while (remaining && n < max_entries) {
+        unsigned ps, pt;
+        if (remaining == max_proc && sai_mask[cst]) { ps = cs; pt = ct; }
+        else {
+            unsigned pst_g = 0;
+            for (unsigned st = 0; st < asize; st++) if (!proc[st]) pst_g = st;
+            if (p->ang_major == LFBM5D_ROWMAJOR) { ps = pst_g / aw; pt = pst_g - ps * aw; }
+            else { pt = pst_g / ah; ps = pst_g - pt * ah; }
+        }
+        int c_s, min_s, max_s, c_t, min_t, max_t;
+        angular_search_window(c_s, min_s, max_s, ps, ah, p->an);
+        angular_search_window(c_t, min_t, max_t, pt, aw, p->an);
+        int level = 0;
+        unsigned nmasked = 0;
+        for (int s = min_s; s <= max_s; s++)
+            for (int t2 = min_t; t2 <= max_t; t2++) {
+                const unsigned st = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) s * aw + t2 : (unsigned) s + (unsigned) t2 * ah;
+                level = std::max(level, last_level[st] + 1);
+                nmasked += sai_mask[st] == 0;
+            }
+        if (nmasked && p->tau_4D == LFBM5D_DCT) sticky = 1;
+        for (int s = min_s; s <= max_s; s++)
+            for (int t2 = min_t; t2 <= max_t; t2++) {
+                const unsigned st = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) s * aw + t2 : (unsigned) s + (unsigned) t2 * ah;
+                last_level[st] = level;
+                if (!proc[st]) proc[st] = 1;
+            }
+        unsigned *e = out + 6 * n;
+        e[0] = ps; e[1] = pt; e[2] = (unsigned) min_s; e[3] = (unsigned) min_t; e[4] = (unsigned) level; e[5] = sticky;
+        n++;
+        remaining = 0;
+        for (unsigned st = 0; st < asize; st++) remaining += proc[st] == 0;
+    }
+    return n;
+}
+
+int lfbm5d_step_force_sadct(lfbm5d_ctx *ctx)
+{
+    if (!ctx || !ctx->ss.active) return fail("no step in progress");
+    if (ctx->ss.tau_4D == LFBM5D_DCT) ctx->ss.tau_4D = LFBM5D_SADCT;      // the window code reloads the tables when it differs
+    return 0;
+}
+
 unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries)
 {
     if (!ctx) return 0;
