@@ -219,6 +219,27 @@ def run_ours(args):
         e2e = {"value": world * lf_pix * frac_passes / (float(t_e2e.item()) / args.steps) / 1e6, "unit": "LF Mpix/s",
                "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": 5 * nbytes, "timer": "host wall clock around the C ABI calls, max over ranks"}
 
+    # ---- strong scaling (N > 1): ONE light field on all ranks, windows that share no SAI on different GPUs, accumulators
+    # broadcast over NCCL per plan level (lfbm5d_b200/dist.py); bit-identical to the single-GPU result. Reported beside the
+    # weak-scaling headline, not instead of it.
+    strong = None
+    if world > 1 and not args.passes and not args.no_strong:
+        from lfbm5d_b200 import dist as D
+        t_strong = []
+        for it in range(2):                                   # one warm-up (buffers, NCCL), one timed
+            work.copy_(noisy0)
+            barrier()
+            t0 = time.perf_counter()
+            D.run_step_windows(eng, 1, p1, work.data_ptr(), 0, mask, basic.data_ptr(), dist, dev)
+            plan = D.run_step_windows(eng, 2, p2, work.data_ptr(), basic.data_ptr(), mask, out.data_ptr(), dist, dev)
+            barrier()
+            t_strong.append(time.perf_counter() - t0)
+        ts = torch.tensor([t_strong[-1]], device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"value": lf_pix / float(ts.item()) / 1e6, "unit": "LF Mpix/s", "seconds": float(ts.item()),
+                  "speedup_vs_one_gpu": (ms_per_step * 1e-3) / float(ts.item()), "plan_levels": int(plan[:, 4].max()) + 1,
+                  "windows": int(len(plan)), "note": "one light field, window-level parallelism, results identical to one GPU"}
+
     # ---- per-kernel timing for the roofline (separate short run with per-phase CUDA events on the library's stream) ----
     roof, roof_other, roof_bm, phases = None, None, None, None
     if rank == 0 and args.profile_passes > 0:
@@ -282,7 +303,7 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "per_rank": "one full light field per GPU (replicas; no data-path collective)",
                            "l2": "inputs (3.6 GB per buffer) larger than L2", "passes_per_step": args.passes or N_PASSES},
                 "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "roofline_other": roof_other, "roofline_bm": roof_bm,
-                "phases": phases, "cpu_baseline": cpu, "psnr": {"noisy": psnr_in, "denoised": psnr_out}}
+                "phases": phases, "strong_scaling": strong, "cpu_baseline": cpu, "psnr": {"noisy": psnr_in, "denoised": psnr_out}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -367,6 +388,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--passes", type=int, default=0, help="debug: stop each step after this many window passes (value is scaled)")
     ap.add_argument("--profile-passes", type=int, default=4)
+    ap.add_argument("--no-strong", action="store_true", help="skip the one-light-field strong-scaling measurement at N > 1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

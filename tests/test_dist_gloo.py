@@ -47,3 +47,44 @@ def test_shard_gather_max_over_ranks():
         assert p.exitcode == 0
     assert ret[0][0] and ret[1][0] and ret[0][1] == 2.0 and ret[1][1] == 2.0
     assert (ret[0][2], ret[0][3], ret[1][2], ret[1][3]) == (0, 5, 5, 9)
+
+
+def test_window_plan_matches_the_sequential_schedule(oracle):
+    """lfbm5d_step_plan (static form of the reference's window selection) against the schedule the oracle's step driver takes
+    (itself bit-identical to the reference), with and without empty SAIs; windows of one level share no SAI."""
+    import lfbm5d_b200 as L
+    from lfbm5d_b200 import dist as D
+    import lfdata
+    for (aw, ah, holes, major) in [(5, 5, (), L.ROWMAJOR), (7, 5, (3, 17), L.ROWMAJOR), (6, 4, (23,), L.COLMAJOR)]:
+        clean = lfdata.synth_lf(aw, ah, 12, 12)
+        noisy = oracle.add_noise(clean, 10.0)
+        mask = np.ones(aw * ah, np.uint32)
+        for h in holes:
+            mask[h] = 0
+        _, _, sched = oracle.run_step1(noisy, mask, 10.0, 2.7, aw, ah, 1, 2, 2, 1, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR, ang_major=major)
+        prm = L.make_params(10.0, 2.7, aw, ah, 1, 12, 12, 3, 2, 2, 1, 8, 4, L.ID, L.DCT, L.HAAR, ang_major=major)
+        plan = L.step_plan(prm, mask)
+        assert len(plan) == len(sched)
+        assert np.array_equal(plan[:, 2:4], sched[:, 1:3])                       # same windows in the same order
+        seen = np.zeros(aw * ah, bool)
+        for lvl in D.plan_levels(plan):
+            used = []
+            for w in lvl:
+                used += D.window_sais(w, prm, mask)
+            assert len(used) == len(set(used))                                   # windows of a level are disjoint
+            seen[used] = True
+        assert np.array_equal(seen, mask.astype(bool))
+        if holes:                                                               # sticky dct -> sadct switch from the first window with a hole
+            first = min(i for i, w in enumerate(plan) if any(not mask[st] for st in _window_all(w, prm)))
+            assert np.array_equal(plan[:, 5], (np.arange(len(plan)) >= first).astype(np.uint32))
+        owners = [D.window_owner(lvl, 3) for lvl in D.plan_levels(plan)]
+        assert all(o == list(range(len(o))) or max(o) < 3 for o in owners)
+
+
+def _window_all(w, prm):
+    import lfbm5d_b200 as L
+    out = []
+    for s in range(int(w[2]), int(w[2]) + 3):
+        for t in range(int(w[3]), int(w[3]) + 3):
+            out.append(s * int(prm.awidth) + t if int(prm.ang_major) == L.ROWMAJOR else s + t * int(prm.aheight))
+    return out
