@@ -182,11 +182,23 @@ def run_ours(args):
 
     # ---- e2e: host-buffer C ABI with pinned memory, copies inside the timed region ----
     e2e = None
+    e2e_ok = 0
     if not args.no_e2e:
-        h_noisy = torch.empty(noisy0.shape, pin_memory=True)
-        h_noisy0 = noisy0.cpu().pin_memory()
-        h_basic = torch.empty(noisy0.shape, pin_memory=True)
-        h_out = torch.empty(noisy0.shape, pin_memory=True)
+        try:        # 3 x 3.6 GB of pinned host memory per rank; every rank has to get it, or all skip the measurement
+            h_noisy = torch.empty(noisy0.shape, pin_memory=True)
+            h_basic = torch.empty(noisy0.shape, pin_memory=True)
+            h_out = torch.empty(noisy0.shape, pin_memory=True)
+            h_noisy0 = noisy0.cpu()
+            e2e_ok = 1
+        except RuntimeError:
+            e2e_ok = 0
+        if world > 1:
+            f = torch.tensor([e2e_ok], device=dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN)
+            e2e_ok = int(f.item())
+        if not e2e_ok:
+            e2e = {"value": None, "unit": "LF Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": "pinned host allocation failed"}
+    if e2e_ok:
         del clean
         torch.cuda.empty_cache()
 
