@@ -494,13 +494,18 @@ __global__ void k_active_refs(const float *__restrict__ den0, const int *__restr
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    const float *pp = den0 + (size_t) rows[r / nc] * w + cols[r % nc];
+    const int ry = rows[r / nc], rx = cols[r % nc];
+    const float *pp = den0 + (size_t) ry * w + rx;
     bool open = false;
     for (int p = 0; p < k && !open; ++p)
         for (int q = 0; q < k; ++q)
             if (pp[p * w + q] == 0.0f) { open = true; break; }
     act[r] = open ? 1 : 0;
-    if (open) atomicAdd(count, 1u);
+    if (open) {      // count[1], count[2]: last row / column of an active reference patch (block matching stops behind them)
+        atomicAdd(count, 1u);
+        atomicMax(count + 1, (unsigned) ry);
+        atomicMax(count + 2, (unsigned) rx);
+    }
 }
 
 // bit st of gmask[r]: SAI st belongs to the angular shape of reference patch r (core:300-312)

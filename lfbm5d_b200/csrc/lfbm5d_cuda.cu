@@ -388,18 +388,20 @@ int ensure_shape_lut(lfbm5d_ctx *ctx, unsigned asw)
 int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, int cst = -1)
 {
     const bool partial = cst >= 0 && cst != pst;
+    int act_ymax = -1, act_xmax = -1;       // partial-window branch: last row / column of a reference patch that is still processed
     if (partial) {
         const size_t Rr = pc.rows.size() * pc.cols.size();
-        if (ctx->act.ensure(Rr + 8)) return 1;
+        if (ctx->act.ensure(Rr + 16)) return 1;
         unsigned *cnt = reinterpret_cast<unsigned *>(ctx->act.as<unsigned char>() + ((Rr + 3) & ~(size_t) 3));
-        CK(cudaMemsetAsync(cnt, 0, 4, ctx->stream));
+        CK(cudaMemsetAsync(cnt, 0, 12, ctx->stream));
         LAUNCH(ctx, k_active_refs, (unsigned) ((Rr + 255) / 256), 256, 0,
                ctx->densym.as<float>() + (size_t) pst * pc.C * pc.wb * pc.hb, ctx->rows.as<int>(), ctx->cols.as<int>(), (int) pc.cols.size(), (int) Rr,
                (int) pc.wb, (int) pc.k, ctx->act.as<unsigned char>(), cnt);
-        unsigned h = 0;
-        CK(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned h3[3] = { 0, 0, 0 };
+        CK(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (h == 0) return 0;       // nothing left to denoise in this SAI (core:160-165)
+        if (h3[0] == 0) return 0;       // nothing left to denoise in this SAI (core:160-165)
+        act_ymax = (int) h3[1]; act_xmax = (int) h3[2];
     }
     const size_t plane = (size_t) pc.wb * pc.hb;
     const int nr = (int) pc.rows.size(), nc = (int) pc.cols.size(), R = nr * nc;
@@ -432,9 +434,15 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
             groups.push_back(G);
         }
     const int nself_groups = (int) groups.size(), nself_planes = (int) planes.size();
-    const int st_lo = pc.nDisp, st_row_end = pc.hb - pc.nDisp - pc.k + 1, st_col_end = pc.wb - pc.nDisp - pc.k + 1;
+    // The summed-area recurrences run from the top-left corner, so stopping them early changes nothing in what was computed.
+    // The partial-window branch needs the self sums up to the last active reference patch (+ nSim columns for the mirrored
+    // offsets) and the disparity results up to nSim rows / columns further (positions of the self matches); the reference
+    // computes the whole planes there as well (core:3631-3788, :3806-3945) and reads the same values.
+    const int st_lo = pc.nDisp, st_row_full = pc.hb - pc.nDisp - pc.k + 1, st_col_full = pc.wb - pc.nDisp - pc.k + 1;
+    const int st_row_end = partial ? std::min(st_row_full, act_ymax + (int) pc.nSim + 1) : st_row_full;
+    const int st_col_end = partial ? std::min(st_col_full, act_xmax + (int) pc.nSim + 1) : st_col_full;
     const int st_strips = (st_col_end - st_lo + 31) / 32, st_SR = (st_row_end - st_lo) + 31;
-    const size_t st_stride = (size_t) st_strips * st_SR * 32;
+    const size_t st_stride = (size_t) ((st_col_full - st_lo + 31) / 32) * ((st_row_full - st_lo) + 31) * 32;      // allocation: full planes
     int slot = 0;
     for (int st = 0; st < (int) pc.A; st++) {
         if (st == pst || !win.mask[st]) continue;
@@ -458,7 +466,9 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
         CK(cudaMemcpyAsync(ctx->satplanes.p, planes.data(), planes.size() * sizeof(SatPlane), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->satgroups.p, groups.data(), groups.size() * sizeof(SatGroup), cudaMemcpyHostToDevice, ctx->stream));
     }
-    const int self_strips = ((int) pc.wb - 2 * (int) pc.n + 31) / 32;
+    const int self_row_end = partial ? std::min((int) pc.hb - (int) pc.n, act_ymax + 1) : (int) pc.hb - (int) pc.n;
+    const int self_col_end = partial ? std::min((int) pc.wb - (int) pc.n, act_xmax + (int) pc.nSim + 1) : (int) pc.wb - (int) pc.n;
+    const int self_strips = (self_col_end - (int) pc.n + 31) / 32;
     int *ticket = ctx->progress.as<int>();      // [0]: self launch, [1]: stereo launch; flags follow
     int *flags = ticket + 4;
     CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) std::max(self_strips, st_strips)) * 4, ctx->stream));
@@ -487,7 +497,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     if (nself > 0) {
         LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
         SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = pc.hb - pc.n; g.col_end = pc.wb - pc.n;
+        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = self_row_end; g.col_end = self_col_end;
         g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.SR = 0;
         g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
         g.gp = pc.p; g.nr = nr; g.rlast = pc.rows.back();
