@@ -783,7 +783,10 @@ __global__ void k_stereo_ties(TieGeom g, const float *__restrict__ sums, const u
         const int i = g.lo + sidx - lane, j = g.lo + (strip << 5) + lane;
         const int k_r = i * g.w + j;
         const float *sp = sums + (size_t) en.x * np * g.plane_stride + t;
-        LfPair td[LF_MAXNS2];
+        // the pairs live in shared memory: the emulated sort is a chain of dependent accesses (one thread per position, few
+        // positions), its time is memory latency
+        extern __shared__ LfPair s_td[];
+        LfPair *td = s_td + (size_t) threadIdx.x * LF_MAXNS2;
         int c = 0;
         for (int djx = 0; djx < Ns; ++djx)
             for (int dix = 0; dix < Ns; ++dix, ++c) {

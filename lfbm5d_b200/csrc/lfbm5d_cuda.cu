@@ -559,7 +559,9 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
                    (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
                    ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned) s, sl, sc);
         }
-        LAUNCH_ON(ctx, sB, k_stereo_ties, ctx->num_sms * 8, 64, 0, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
+        const size_t smem_t = (size_t) 32 * LF_MAXNS2 * sizeof(LfPair);
+        CK(cudaFuncSetAttribute((const void *) k_stereo_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
+        LAUNCH_ON(ctx, sB, k_stereo_ties, ctx->num_sms * 4, 32, smem_t, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
                   ctx->first.as<unsigned>());
     }
     CK(cudaEventRecord(ctx->ev_join, sB));
