@@ -58,3 +58,38 @@ def test_cli_readme_command(tmp_path):
     args2[1] = "none"
     p = subprocess.run(args2, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
     assert p.returncode == 0 and b"Loading noisy LF elapsed time" in p.stdout
+
+
+@pytest.mark.gpu
+def test_cli_grayscale_and_lfbm3d(tmp_path):
+    """Grayscale PNGs through LFBM5Ddenoising (every window takes several core calls: the partial-window branch) and the
+    LFBM3Ddenoising driver (31 positional arguments of main_bm3d_LF.cpp, README.md:62 parameters) on RGB PNGs."""
+    from PIL import Image
+    clean = lfdata.synth_lf(3, 3, 48, 56)
+    env = dict(os.environ, LFBM5D_SEED="7")
+    for tag in ("gray", "rgb"):
+        base = tmp_path / tag
+        base.mkdir()
+        for d in ("sourceLF", "noisyLF", "basicLF", "denoisedLF", "diffLF"):
+            (base / d).mkdir()
+        for s in range(3):
+            for t in range(3):
+                img = np.clip(np.floor(clean[s * 3 + t] + 0.5), 0, 255).astype(np.uint8)
+                im = Image.fromarray(img[0]) if tag == "gray" else Image.fromarray(img.transpose(1, 2, 0))
+                im.save(str(base / "sourceLF" / ("SAI_%02d_%02d.png" % (s + 1, t + 1))))
+        report = base / "results.txt"
+        dirs = [str(base / d) for d in ("noisyLF", "basicLF", "denoisedLF", "diffLF")]
+        if tag == "gray":
+            args = [os.path.join(LIBDIR, "LFBM5Ddenoising"), str(base / "sourceLF"), "SAI", "_", "3", "3", "1", "1", "1", "1", "row", "20", "2.7"] + dirs + \
+                   ["8", "18", "6", "16", "4", "id", "sadct", "haar", "0", "16", "18", "6", "8", "4", "dct", "sadct", "haar", "0", "opp", "0", str(report)]
+        else:
+            args = [os.path.join(LIBDIR, "LFBM3Ddenoising"), str(base / "sourceLF"), "SAI", "_", "3", "3", "1", "1", "1", "1", "row", "20", "2.7"] + dirs + \
+                   ["16", "16", "8", "3", "bior", "0", "32", "16", "8", "3", "dct", "0", "opp", "0", str(report)]
+        p = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=300)
+        out = p.stdout.decode()
+        assert p.returncode == 0, out[-2000:]
+        assert len(os.listdir(dirs[2])) == 9
+        vals = [float(x) for x in re.findall(r"-> Average PSNR \w+ = ([0-9.]+)", report.read_text())]
+        assert len(vals) == 3 and vals[2] - vals[0] > 4.0, vals
+        den = np.asarray(Image.open(os.path.join(dirs[2], "SAI_02_02.png")), dtype=np.float32)
+        assert den.shape == ((48, 56) if tag == "gray" else (48, 56, 3))
