@@ -77,6 +77,18 @@ def test_window_plan_matches_the_sequential_schedule(oracle):
         if holes:                                                               # sticky dct -> sadct switch from the first window with a hole
             first = min(i for i, w in enumerate(plan) if any(not mask[st] for st in _window_all(w, prm)))
             assert np.array_equal(plan[:, 5], (np.arange(len(plan)) >= first).astype(np.uint32))
+        for world in (1, 2, 3, 8):                                                # list scheduling: every window once, dependencies first
+            order = {}
+            for ri, rnd in enumerate(D.plan_rounds(plan, prm, world)):
+                assert 1 <= len(rnd) <= world
+                for w in rnd:
+                    order[(int(w[2]), int(w[3]))] = ri
+            assert len(order) == len(plan)
+            for i, wi in enumerate(plan):
+                for wj in plan[:i]:
+                    if set(_window_all(wi, prm)) & set(_window_all(wj, prm)):
+                        assert order[(int(wj[2]), int(wj[3]))] < order[(int(wi[2]), int(wi[3]))]
+        assert D.sai_ranges([4, 5, 6, 9, 11, 12]) == [[4, 7], [9, 10], [11, 13]]
         owners = [D.window_owner(lvl, 3) for lvl in D.plan_levels(plan)]
         assert all(o == list(range(len(o))) or max(o) < 3 for o in owners)
 
