@@ -1,4 +1,4 @@
-// Block matching: exact float32 summed-area recurrences (one warp sweeps one offset plane as a skewed
+// Block matching: exact float32 summed-area recurrences (a warp sweeps two offset planes as a skewed
 // wavefront), top-N selection for self similarity and argmin for disparity matching, with the libstdc++
 // sort algorithms emulated where exact float ties make the reference's result algorithm-dependent.
 //
@@ -46,18 +46,15 @@ template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
     return v;
 }
 
-// Summed-area planes, v2. Work unit = (group of <= 13 planes sharing their source rows, 32-column strip): one warp
-// per plane; lane l owns column c0+l and runs one row behind lane l-1 (skewed wavefront, one shuffle per step).
-// The strips of a plane are pipelined across CTAs: strip c consumes the last column of strip c-1 through global
-// memory with a per-(plane, strip) progress flag, and CTAs take their work from a ticket counter in strip-major
-// order so that a producer has always started before its consumer (no deadlock). Source rows of both images are
-// staged once per CTA with cp.async into two 128-row shared-memory rings (row stride 64 floats: the skewed reads
-// are bank-conflict free) and reused by all planes of the group; squared differences are formed on the fly.
-// ---- packed FP32x2 arithmetic (FADD2 / FMUL2 on sm_100): two planes per lane, IEEE per half ----
-
-// Summed-area planes, v3. As v2, with TWO planes per lane (column offsets ox and ox+1 of the same group): the img1
-// operand is shared, the img2 operands are adjacent ring entries, and all floating-point work of the step runs as packed
-// FP32x2 instructions (bit-identical per half), which halves the issue slots of the issue-bound inner loop.
+// Summed-area planes. Work unit = (group of <= 2 * SAT_NW planes sharing their source rows, 32-column strip). A warp sweeps
+// TWO planes (column offsets ox and ox + 1 of the group): lane l owns column c0 + l and runs one row behind lane l - 1 (skewed
+// wavefront, one 64-bit shuffle per step); the img1 operand is shared, the img2 operands are adjacent ring entries, and all
+// floating-point work of a step runs as packed FP32x2 instructions (bit-identical per half).
+// The strips of a plane are pipelined across CTAs: strip c consumes the last column of strip c - 1 through global memory with
+// a per-(plane, strip) progress flag, and CTAs take their work from a ticket counter in strip-major order so that a producer
+// has always started before its consumer (no deadlock). Source rows of both images are staged once per CTA with cp.async
+// into two 128(+K)-row shared-memory rings (row stride 64 floats: the skewed reads are bank-conflict free) and reused by all
+// planes of the group; squared differences are formed on the fly.
 template <bool SELF, int K>
 __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
                                                           int ngroups, float *bnd, int *progress, int *ticket_counter)
