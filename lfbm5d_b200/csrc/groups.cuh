@@ -1,6 +1,8 @@
 // 5-D group processing: gather -> 2-D spatial transform -> angular (SA-)DCT -> 1-D transform along the similar
-// patches -> hard threshold / Wiener shrinkage -> inverses -> weighted aggregation. One CTA per reference patch,
-// one colour channel at a time in shared memory. Restates core:277-528 (step 1) and :1054-1329 (step 2).
+// patches -> hard threshold / Wiener shrinkage -> inverses (group kernels, one CTA per reference patch: the generic
+// k_groups with one colour channel at a time in shared memory, the register-resident k_groups_id16, and the packed
+// k_groups_w8 in groups_wiener8.cuh), then the ordered weighted aggregation of the staged patches (k_aggregate).
+// Restates core:277-528 (step 1) and :1054-1329 (step 2).
 #pragma once
 #include "common.cuh"
 
