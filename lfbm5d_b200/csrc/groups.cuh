@@ -948,37 +948,38 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
     if (a_hi >= a_lo && nbn > 0) {
         const unsigned *ent = g.ent + (size_t) st * g.R * N;
         int total = 0, buf = 0;            // entries listed so far (identical in every thread)
-        for (int a = a_lo; a <= a_hi; ++a) {
-            const unsigned *erow = ent + ((size_t) a * g.nc + b_lo) * N;      // candidates (b, n) of this reference row are contiguous
-            for (int base = 0; base < nbn; base += 256) {
-                if (total + 256 > AGG_CAP - 1) { flush(total); total = 0; }
-                // ---- candidates (a, b, n) in the reference's order; keep those whose patch covers the tile ----
-                const int bn = base + tid;
-                bool hit = false;
-                unsigned yx = 0;
-                if (bn < nbn) {
-                    yx = __ldg(erow + bn);
-                    const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);       // LF_NOENT: far outside
-                    hit = py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) wcount[buf][warp] = __popc(m);
-                __syncthreads();
-                int off = total;
-#pragma unroll
-                for (int wv = 0; wv < 8; ++wv) { const int cw = wcount[buf][wv]; if (wv < warp) off += cw; total += cw; }
-                if (hit) {
-                    const int o = off + __popc(m & ((1u << lane) - 1u));
-                    const int rn = (a * g.nc + b_lo) * N + bn;       // r * N + n
-                    const int r = rn >> g.log2N;
-                    lpos[o] = make_uint2(yx, (unsigned) (((size_t) rn * A + st) * C));
-                    float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
-                    ew.x = g.wbuf[(size_t) r * C];
-                    if (C > 1) { ew.y = g.wbuf[(size_t) r * C + 1]; ew.z = g.wbuf[(size_t) r * C + 2]; }
-                    lw[o] = ew;
-                }
-                buf ^= 1;
+        // candidates (a, b, n) in the reference's order, flattened: f = (a - a_lo) * nbn + (b - b_lo) * N + n; the (b, n) of a
+        // reference row are contiguous in ent. 256 candidates per round, whatever the row length.
+        const int nf = (a_hi - a_lo + 1) * nbn;
+        for (int base = 0; base < nf; base += 256) {
+            if (total + 256 > AGG_CAP - 1) { flush(total); total = 0; }
+            const int f = base + tid;
+            bool hit = false;
+            unsigned yx = 0;
+            int rn = 0;
+            if (f < nf) {
+                const int da = f / nbn, bn = f - da * nbn;
+                rn = ((a_lo + da) * g.nc + b_lo) * N + bn;       // r * N + n
+                yx = __ldg(ent + rn);
+                const int py = (int) (yx >> 16), px = (int) (yx & 0xffffu);       // LF_NOENT: far outside
+                hit = py < y0 + 16 && py + k > y0 && px < x0 + 16 && px + k > x0;       // keep those whose patch covers the tile
             }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) wcount[buf][warp] = __popc(m);
+            __syncthreads();
+            int off = total;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) { const int cw = wcount[buf][wv]; if (wv < warp) off += cw; total += cw; }
+            if (hit) {
+                const int o = off + __popc(m & ((1u << lane) - 1u));
+                const int r = rn >> g.log2N;
+                lpos[o] = make_uint2(yx, (unsigned) (((size_t) rn * A + st) * C));
+                float4 ew = make_float4(0.f, 0.f, 0.f, 0.f);
+                ew.x = g.wbuf[(size_t) r * C];
+                if (C > 1) { ew.y = g.wbuf[(size_t) r * C + 1]; ew.z = g.wbuf[(size_t) r * C + 2]; }
+                lw[o] = ew;
+            }
+            buf ^= 1;
         }
         flush(total);
     }
