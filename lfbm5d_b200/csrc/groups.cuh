@@ -851,12 +851,14 @@ struct AggArgs {
     const int *arange, *brange;    // per tile row / tile column: first and last candidate reference row / column index
     LfWindow win;
 };
-#define AGG_CAP 768
+#define AGG_CAP_K8 1024     // list capacity for k = 8 (more, smaller patches per tile: one flush per tile) ...
+#define AGG_CAP_K16 768     // ... and otherwise (measured: 768 is faster for k = 16, 1024 for k = 8)
 
 // K, CC: compile-time patch size / channel count (0 = take them from the arguments)
 template <int K, int CC>
 __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
 {
+    constexpr int AGG_CAP = K == 8 ? AGG_CAP_K8 : AGG_CAP_K16;
     __shared__ uint2 lpos[AGG_CAP];                  // (y << 16 | x) of the patch, index of its first channel in zbuf (units of k^2)
     __shared__ float4 lw[AGG_CAP];                   // per-channel weights of its group
     __shared__ unsigned short wlist[8][AGG_CAP];     // per warp: the listed patches that touch the warp's 8x4 pixels, in list order
