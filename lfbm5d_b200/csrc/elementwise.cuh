@@ -122,9 +122,16 @@ __global__ void k_est0(const float *__restrict__ sub, const float *__restrict__ 
 }
 
 // Crop the accumulators back (bm5d.cpp:388-396).
+__device__ __forceinline__ unsigned long long lf_block_sum_u64(unsigned long long v);
+
+// Crop the padded accumulators of the window back into the light field (bm5d.cpp:388-396). With `count` it also counts the
+// entries with den > 0 in the top-left (H-k+1) x (W-k+1) of every SAI (LF_denoised_percent, utilities_LF.cpp:967-995): the
+// step driver runs it after every core call, so the coverage test costs no extra pass over the accumulators.
 __global__ void k_unpad_window(float *__restrict__ num, float *__restrict__ den, const float *__restrict__ numsym,
-                               const float *__restrict__ densym, LfWindow win, int W, int H, int C, int n)
+                               const float *__restrict__ densym, LfWindow win, int W, int H, int C, int n, int k = 0,
+                               unsigned long long *count = nullptr)
 {
+    unsigned long long cnt = 0;
     const int wb = W + 2 * n, hb = H + 2 * n;
     const size_t plane_b = (size_t) wb * hb, plane = (size_t) W * H;
     const size_t total = (size_t) win.A * C * plane;
@@ -137,8 +144,14 @@ __global__ void k_unpad_window(float *__restrict__ num, float *__restrict__ den,
         const int i = (int) (px / W), j = (int) (px - (size_t) i * W);
         const size_t src = ((size_t) a * C + c) * plane_b + (size_t) (i + n) * wb + (j + n);
         const size_t dst = ((size_t) win.st[a] * C + c) * plane + px;
+        const float dv = densym[src];
         num[dst] = numsym[src];
-        den[dst] = densym[src];
+        den[dst] = dv;
+        if (count && i < H - k + 1 && j < W - k + 1 && dv > 0.0f) cnt++;
+    }
+    if (count) {
+        cnt = lf_block_sum_u64(cnt);
+        if (threadIdx.x == 0 && cnt) atomicAdd(count, cnt);
     }
 }
 
@@ -153,28 +166,6 @@ __device__ __forceinline__ unsigned long long lf_block_sum_u64(unsigned long lon
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     }
     return v;
-}
-
-// Number of (pixel, channel) entries with den > 0 in the top-left (H-k+1)x(W-k+1) interior of every window SAI
-// (utilities_LF.cpp:967-995). The host applies the reference's float saturation and normalisation.
-__global__ void k_count_denoised(const float *__restrict__ densym, LfWindow win, int W, int H, int C, int n, int k,
-                                 unsigned long long *out)
-{
-    const int wb = W + 2 * n, hb = H + 2 * n, hh = H - k + 1, ww = W - k + 1;
-    const size_t plane_b = (size_t) wb * hb;
-    const size_t per = (size_t) hh * ww * C, total = (size_t) win.A * per;
-    unsigned long long cnt = 0;
-    for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
-        const int a = (int) (t / per);
-        if (!win.mask[a]) continue;
-        size_t r = t - (size_t) a * per;
-        const int c = (int) (r / ((size_t) hh * ww));
-        r -= (size_t) c * hh * ww;
-        const int i = (int) (r / ww), j = (int) (r - (size_t) i * ww);
-        if (densym[((size_t) a * C + c) * plane_b + (size_t) (i + n) * wb + (j + n)] > 0.0f) cnt++;
-    }
-    cnt = lf_block_sum_u64(cnt);
-    if (threadIdx.x == 0 && cnt) atomicAdd(out, cnt);
 }
 
 // Number of entries equal to 0.0 in the accumulator of one SAI (bm5d.cpp:195).

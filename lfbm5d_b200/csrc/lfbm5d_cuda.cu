@@ -841,8 +841,9 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
         proc[win.st[pst_asw]] += 1;
         // LF_denoised_percent (utilities_LF.cpp:967-995): float counter (saturates at 2^24), normalised without C
         CK(cudaMemsetAsync(counters, 0, 8, ctx->stream));
-        LAUNCH(ctx, k_count_denoised, grid_for(ctx, (size_t) Aw * C * (H - pc.k + 1) * (W - pc.k + 1)), 256, 0, ctx->densym.as<float>(),
-               win, (int) W, (int) H, (int) C, (int) pc.n, (int) pc.k, counters);
+        // crop the accumulators back into the light field and count the covered entries in the same pass over them
+        LAUNCH(ctx, k_unpad_window, grid_for(ctx, (size_t) Aw * each), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
+               ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, (int) pc.k, counters);
         unsigned long long cnt = 0;
         CK(cudaMemcpyAsync(&cnt, counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -856,8 +857,7 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
         n_unproc = 0;
         for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
     }
-    LAUNCH(ctx, k_unpad_window, grid_for(ctx, (size_t) Aw * each), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
-           ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
+    // (the accumulators were cropped back after every core call)
     for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) touched[win.st[a]] = 1;
     ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
     ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
