@@ -102,6 +102,9 @@ void lfbm5d_set_max_passes(lfbm5d_ctx *ctx, unsigned max_passes);
  * (lfbm5d_b200/dist.py). Results are those of the sequential order. */
 int lfbm5d_step_begin(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_noisy_io, float *d_basic_io, const unsigned *sai_mask);
 int lfbm5d_step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt);                 /* window centred (clamped) on SAI (s, t) = (ps, pt) */
+/* same, with the dct -> sadct switch of the window taken from the plan entry (column `sadct`) instead of the context's sticky
+ * state: what a driver that runs the windows out of their sequential order has to use (bm5d.cpp:276-280) */
+int lfbm5d_step_window_ex(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, int sadct);
 int lfbm5d_step_end(lfbm5d_ctx *ctx, float *d_out);
 int lfbm5d_step_accumulators(lfbm5d_ctx *ctx, float **d_num, float **d_den, size_t *floats_per_sai);
 /* out[6 * i + ...] = (ps, pt, first s of the window, first t, level, sadct) of window i; returns the number of windows */
@@ -123,6 +126,11 @@ int lfbm5d_debug_pass(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const f
 int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *noisy_sym, const float *basic_sym,
                          float *num_sym_io, float *den_sym_io, const unsigned *mask_asw, const unsigned *procSAI_asw, unsigned cst,
                          unsigned pst, unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
+/* Block matching alone (precompute_BM, bm5d_core_processing.cpp:3301-3461, and precompute_BM_stereo, :3479-3611) on HOST channel-0
+ * planes [nplanes][h_b*w_b]: plane 0 is the reference SAI, planes 1.. are matched against it. Outputs as in lfbm5d_debug_pass
+ * (count / idx of plane 0; first / shape [nplanes][h_b*w_b], rows of plane 0 unused). For parity tests at full plane sizes. */
+int lfbm5d_debug_block_matching(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *planes, unsigned nplanes,
+                                unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape);
 /* Window schedule of the last step call: (processed st, min_s, min_t, core calls) per window pass. */
 unsigned lfbm5d_debug_schedule(lfbm5d_ctx *ctx, unsigned *out, unsigned max_entries);
 

@@ -45,9 +45,53 @@ EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset
            "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
            "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_pass_ex",
            "lfbm5d_debug_schedule", "lfbm5d_step_begin", "lfbm5d_step_window", "lfbm5d_step_end", "lfbm5d_step_accumulators",
-           "lfbm5d_step_plan", "lfbm5d_step_force_sadct"]
+           "lfbm5d_step_plan", "lfbm5d_step_force_sadct", "lfbm5d_step_window_ex", "lfbm5d_debug_block_matching"]
+
+HOST_LIB_PATH = os.path.join(_HERE, "_lib", "liblfbm5d_host.so")
+HOST_EXPORTS = ["lfio_add_noise", "lfio_psnr"]           # include/lfbm5d_host_c.h
 
 _lib = None
+_host = None
+
+
+def load_host_library():
+    """liblfbm5d_host.so: C++ adapters with the reference's signatures + the C exports of include/lfbm5d_host_c.h."""
+    global _host
+    if _host is None:
+        load_library()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError("%s not found: run __graft_entry__.build()" % HOST_LIB_PATH)
+        _host = C.CDLL(HOST_LIB_PATH)
+    return _host
+
+
+def add_noise(clean, sigma, seed0=20171016, threads=None):
+    """The reference's host noise (utilities.cpp:154-185, mt19937ar + Box-Muller): SAI st uses its own generator seeded
+    seed0 + st; unclipped float32. clean [asize, C, H, W]. SAIs are independent, so they are generated on `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    h = load_host_library()
+    src = np.ascontiguousarray(clean, np.float32)
+    out = np.empty_like(src)
+
+    def one(st):
+        h.lfio_add_noise(_fp(src[st]), _fp(out[st]), C.c_size_t(src[st].size), C.c_float(sigma), C.c_ulong(seed0 + st))
+    with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(one, range(src.shape[0])))
+    return out
+
+
+def psnr(a, b):
+    """compute_psnr (utilities.cpp:412-435) of two images -> (psnr, rmse)."""
+    h = load_host_library()
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    p, r = C.c_float(), C.c_float()
+    h.lfio_psnr(_fp(a), _fp(b), C.c_size_t(a.size), C.byref(p), C.byref(r))
+    return p.value, r.value
+
+
+def psnr_lf(a, b):
+    """Mean over the SAIs of the per-SAI PSNR (compute_psnr_LF, utilities_LF.cpp:639-700)."""
+    return float(np.mean([psnr(a[st], b[st])[0] for st in range(a.shape[0])]))
 
 
 def load_library():
@@ -196,8 +240,13 @@ class LFBM5D(object):
         if self.lib.lfbm5d_step_begin(self.ctx, int(step), C.byref(prm), C.c_void_p(d_noisy), C.c_void_p(d_basic or 0), _up(m)) != 0:
             raise RuntimeError("lfbm5d_step_begin: " + self.error())
 
-    def step_window(self, ps, pt):
-        if self.lib.lfbm5d_step_window(self.ctx, int(ps), int(pt)) != 0:
+    def step_window(self, ps, pt, sadct=None):
+        """sadct=None: sequential sticky rule; 0 / 1: the plan's value for this window (out-of-order drivers)."""
+        if sadct is None:
+            rc = self.lib.lfbm5d_step_window(self.ctx, int(ps), int(pt))
+        else:
+            rc = self.lib.lfbm5d_step_window_ex(self.ctx, int(ps), int(pt), int(sadct))
+        if rc != 0:
             raise RuntimeError("lfbm5d_step_window: " + self.error())
 
     def step_end(self, d_out):
@@ -213,6 +262,16 @@ class LFBM5D(object):
         if self.lib.lfbm5d_step_accumulators(self.ctx, C.byref(pn), C.byref(pd), C.byref(each)) != 0:
             raise RuntimeError("lfbm5d_step_accumulators: " + self.error())
         return pn.value, pd.value, each.value
+
+    def debug_block_matching(self, step, prm, planes):
+        """planes [nplanes, hb, wb] channel-0 estimates (plane 0 = reference SAI) -> (count, idx, first, shape)."""
+        pl = np.ascontiguousarray(planes, np.float32)
+        npl, hb, wb = pl.shape
+        cnt, idx = np.zeros(hb * wb, np.uint32), np.zeros((hb * wb, prm.N + 1), np.uint32)
+        first, shape = np.zeros((npl, hb * wb), np.uint32), np.zeros((npl, hb * wb), np.uint32)
+        if self.lib.lfbm5d_debug_block_matching(self.ctx, int(step), C.byref(prm), _fp(pl), npl, _up(cnt), _up(idx), _up(first), _up(shape)) != 0:
+            raise RuntimeError("lfbm5d_debug_block_matching: " + self.error())
+        return cnt, idx, first, shape
 
     # -- parity/debug: one window pass on padded host buffers --------------------------------------
     def debug_pass(self, step, prm, noisy_sym, basic_sym, num_sym, den_sym, mask, proc, pst, debug=False, cst=None):

@@ -17,6 +17,8 @@ struct SatGeom {
     int row_end, col_end;   // one past its last row/column
     int ylim, xlim;         // squared differences are zero for rows >= ylim or columns >= xlim (self: dim - nHW)
     int nstrips;            // 32-column strips
+    int pstrips;            // strips per plane in the hand-off buffers (bnd / progress): the same for every launch that
+                            // shares them, so that disjoint plane ids give disjoint ranges (>= nstrips)
     int SR;                 // skewed rows per strip in the stereo output: (row_end - lo) + 31
     int nc;                 // number of reference-patch columns (self)
     const int *rowmap;      // [h] row -> reference row index or -1 (self)
@@ -85,12 +87,12 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     const int xb1 = c0 - 1, xb2 = c0 - 1 + G.oxmin;
     const int oxo = PA.ox - G.oxmin;                   // column shift of plane A inside the img2 ring (plane B: +1)
     const int ymax = min(g.row_end - 1 + k - 1, h - 1);
-    const size_t pstride = (size_t) g.nstrips * h;
+    const size_t pstride = (size_t) g.pstrips * h;
     float *bnd_prev = bnd + (size_t) pid * pstride + (size_t) (strip > 0 ? strip - 1 : 0) * h;
     float *bnd_next = bnd + (size_t) pid * pstride + (size_t) strip * h;
     const size_t bB = hasB ? pstride : 0;              // offset from plane A's boundary column to plane B's
-    const int *prog_prev = progress + (size_t) pid * g.nstrips + (strip > 0 ? strip - 1 : 0);
-    int *prog_next = progress + (size_t) pid * g.nstrips + strip;
+    const int *prog_prev = progress + (size_t) pid * g.pstrips + (strip > 0 ? strip - 1 : 0);
+    int *prog_next = progress + (size_t) pid * g.pstrips + strip;
 
     auto load_rows = [&](int y0, int y1) {
         if (y1 > ymax) y1 = ymax;

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 namespace {
 
@@ -125,6 +126,13 @@ struct StepState {
     bool docolor = false;
     cudaEvent_t e_begin = nullptr;
     float bm0 = 0.f, gr0 = 0.f;
+    unsigned asize() const { return p.awidth * p.aheight; }
+    size_t each() const { return (size_t) p.width * p.height * p.chnls; }
+    unsigned cst() const      // centre SAI of the light field (bm5d.cpp:182-186)
+    {
+        const unsigned cs = p.aheight / 2, ct = p.awidth / 2;
+        return p.ang_major == LFBM5D_ROWMAJOR ? cs * p.awidth + ct : cs + ct * p.aheight;
+    }
 };
 
 struct lfbm5d_ctx {
@@ -141,11 +149,13 @@ struct lfbm5d_ctx {
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
+    bool bm_only = false;          // lfbm5d_debug_block_matching: a pass stops behind the match tables
     cudaEvent_t ev[5]{};
     unsigned max_passes = 0;
     std::vector<unsigned> sched;
     bool geom_valid = false;
     unsigned geom_key[8]{};
+    LfTables tab;                 // this context's constants; c_tab (one per device) is reloaded when it holds another context's
 };
 
 namespace {
@@ -188,13 +198,34 @@ int validate(const lfbm5d_params *p, int step)
     if (p->ang_major != LFBM5D_ROWMAJOR && p->ang_major != LFBM5D_COLMAJOR) return fail("ang_major must be row or col");
     if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");   // utilities.cpp:588-592
     if (p->height < p->k || p->width < p->k) return fail("image smaller than a patch");
+    // the mirror padding of nSim + nDisp pixels (utilities.cpp:215-263) reflects once
+    if (p->height < p->nSim + p->nDisp || p->width < p->nSim + p->nDisp) return fail("image smaller than the padding nSim + nDisp");
     (void) step;
+    return 0;
+}
+
+// c_tab is one __constant__ object per device, shared by every context (and host thread) of the process. Each context keeps
+// its own tables; before it launches kernels they are compared with what the device holds and reloaded if they differ (after
+// a device-wide synchronisation, so that no kernel of another context is reading the old ones).
+std::mutex g_tab_mu;
+LfTables g_dev_tab[64];
+bool g_dev_tab_valid[64];
+
+int ensure_tables(lfbm5d_ctx *ctx)
+{
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    const int d = ctx->device & 63;
+    if (g_dev_tab_valid[d] && memcmp(&g_dev_tab[d], &ctx->tab, sizeof(LfTables)) == 0) return 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyToSymbol(c_tab, &ctx->tab, sizeof(LfTables), 0, cudaMemcpyHostToDevice));
+    g_dev_tab[d] = ctx->tab;
+    g_dev_tab_valid[d] = true;
     return 0;
 }
 
 int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau_4D, bool bm3d = false)
 {
-    static LfTables T;    // host staging (pageable); copy is synchronous with respect to the host
+    LfTables &T = ctx->tab;
     memset(&T, 0, sizeof(T));
     const int k = (int) p->k, asw = (int) (2 * p->an + 1);
     dct_tables(T.dct2f, T.dct2i, k);
@@ -263,9 +294,7 @@ int setup_tables(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, unsigned tau
         T.coef5inv[lg] = 0.5f * (float) (SQRT2_INV_D) / sqrtf((float) n);
     }
     for (unsigned c = 0; c < p->chnls; c++) T.thr_dct[c] = lambda * T.sigma[c] * 2.0f * (float) (SQRT2_D);   // core:2566
-    CK(cudaMemcpyToSymbolAsync(c_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return ensure_tables(ctx);
 }
 
 int make_passcfg(PassCfg &pc, int step, const lfbm5d_params *p, unsigned tau_4D)
@@ -388,6 +417,7 @@ int ensure_shape_lut(lfbm5d_ctx *ctx, unsigned asw)
 int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, int cst = -1)
 {
     const bool partial = cst >= 0 && cst != pst;
+    if (ensure_tables(ctx)) return 1;
     int act_ymax = -1, act_xmax = -1;       // partial-window branch: last row / column of a reference patch that is still processed
     if (partial) {
         const size_t Rr = pc.rows.size() * pc.cols.size();
@@ -471,7 +501,9 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     const int self_strips = (self_col_end - (int) pc.n + 31) / 32;
     int *ticket = ctx->progress.as<int>();      // [0]: self launch, [1]: stereo launch; flags follow
     int *flags = ticket + 4;
-    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) std::max(self_strips, st_strips)) * 4, ctx->stream));
+    // one plane stride for both launches: they share bnd / progress and are told apart by their plane ids only
+    const int pstrips = std::max(std::max(self_strips, st_strips), 1);
+    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) pstrips) * 4, ctx->stream));
     cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
     if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
     // Self matching (summed-area planes, selection) stays on the main stream; disparity matching (planes, argmin, ties) runs
@@ -484,7 +516,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     if (slot > 0) {
         SatGeom g{};
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
-        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.SR = st_SR;
+        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.pstrips = pstrips; g.SR = st_SR;
         g.gp = 1; g.negzero2 = 0x8000000080000000ull;
         const size_t smem = 2 * (128 + pc.k) * 64 * 4;
         const int ngroups = (int) groups.size() - nself_groups;
@@ -498,7 +530,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
         LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
         SatGeom g{};
         g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = self_row_end; g.col_end = self_col_end;
-        g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.SR = 0;
+        g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.pstrips = pstrips; g.SR = 0;
         g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
         g.gp = pc.p; g.nr = nr; g.rlast = pc.rows.back();
         g.nreg = 0;      // rows produced by the regular stride of ind_initialize (utilities.cpp:697-712)
@@ -570,6 +602,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) R, (int) pc.wb, (unsigned) plane,
            (int) pc.A, (int) pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
     if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (ctx->bm_only) { CK(cudaGetLastError()); return 0; }
 
     // ---- groups ----
     GroupArgs ga{};
@@ -710,34 +743,19 @@ int step_select(lfbm5d_ctx *ctx, unsigned &ps, unsigned &pt)
 {
     StepState &S = ctx->ss;
     const lfbm5d_params *p = &S.p;
-    const int step = S.step;
-    float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
-    const std::vector<unsigned> &mask = S.mask;
-    std::vector<unsigned> &proc = S.proc;
-    std::vector<char> &touched = S.touched;
-    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
-    const unsigned max_proc = S.max_proc;
-    PassCfg &pc = S.pc;
-    const bool docolor = S.docolor;
-    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
-    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
-    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
-    const unsigned C = p->chnls, W = p->width, H = p->height;
-    const size_t HW = (size_t) W * H, each = HW * C;
-    unsigned long long *counters = ctx->counters.as<unsigned long long>();
-    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
-    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
-    (void) H; (void) HW; (void) each; (void) counters;
+    const std::vector<unsigned> &proc = S.proc;
+    const unsigned asize = S.asize(), cs = p->aheight / 2, ct = p->awidth / 2;
+    const size_t each = S.each();
     unsigned pst_g = 0;
-    if (remaining == max_proc && mask[cst]) { ps = cs; pt = ct; }
+    if (S.remaining == S.max_proc && S.mask[S.cst()]) { ps = cs; pt = ct; }
     else {   // bm5d.cpp:189-202: most entries still at 0, ties to the highest index
         long long best = -1;
         std::vector<unsigned> need;
-        for (unsigned st = 0; st < asize; st++) if (!proc[st] && touched[st]) need.push_back(st);
+        for (unsigned st = 0; st < asize; st++) if (!proc[st] && S.touched[st]) need.push_back(st);
         std::vector<unsigned long long> zc(asize, (unsigned long long) each);
         if (!need.empty()) {
             if (ctx->counters.ensure((need.size() + 8) * 8)) return 1;
-            counters = ctx->counters.as<unsigned long long>();
+            unsigned long long *counters = ctx->counters.as<unsigned long long>();
             CK(cudaMemsetAsync(counters, 0, need.size() * 8, ctx->stream));
             for (size_t i = 0; i < need.size(); i++)
                 LAUNCH(ctx, k_count_zero, grid_for(ctx, each), 256, 0, ctx->den.as<float>() + need[i] * each, each, counters + i);
@@ -758,7 +776,9 @@ int step_select(lfbm5d_ctx *ctx, unsigned &ps, unsigned &pt)
 }
 
 // One angular window centred (and clamped) on SAI (ps, pt): bm5d.cpp:204-402
-int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
+// force_sadct: -1 = the sequential rule (a window with an empty SAI turns dct into sadct for the rest of the step,
+// bm5d.cpp:276-280); 0 / 1 = the value the static plan gives for this window (drivers that run the windows out of order)
+int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, int force_sadct = -1)
 {
     StepState &S = ctx->ss;
     const lfbm5d_params *p = &S.p;
@@ -766,20 +786,12 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
     float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
     const std::vector<unsigned> &mask = S.mask;
     std::vector<unsigned> &proc = S.proc;
-    std::vector<char> &touched = S.touched;
-    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
-    const unsigned max_proc = S.max_proc;
+    unsigned &tau_4D = S.tau_4D;
     PassCfg &pc = S.pc;
-    const bool docolor = S.docolor;
-    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
-    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
-    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
+    const unsigned asize = S.asize(), asw = 2 * p->an + 1, Aw = asw * asw;
     const unsigned C = p->chnls, W = p->width, H = p->height;
-    const size_t HW = (size_t) W * H, each = HW * C;
+    const size_t each = S.each();
     unsigned long long *counters = ctx->counters.as<unsigned long long>();
-    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
-    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
-    (void) H; (void) HW; (void) each; (void) counters;
     int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
     angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
     angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
@@ -798,11 +810,12 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
             win.proc[a] = !mask[st];
             n_unproc += mask[st] != 0;
         }
-    if (n_unproc != Aw && tau_4D == LFBM5D_DCT) tau_4D = LFBM5D_SADCT;
-    if (tau_4D != tables_tau4) {
+    if (force_sadct >= 0) tau_4D = (force_sadct && p->tau_4D == LFBM5D_DCT) ? (unsigned) LFBM5D_SADCT : p->tau_4D;
+    else if (n_unproc != Aw && tau_4D == LFBM5D_DCT) tau_4D = LFBM5D_SADCT;
+    if (tau_4D != S.tables_tau4) {
         pc.tau_4D = tau_4D;
         if (setup_tables(ctx, step, p, tau_4D)) return 1;
-        tables_tau4 = tau_4D;
+        S.tables_tau4 = tau_4D;
     }
     LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) Aw * pc.wb * pc.hb), 256, 0, d_noisy, step == 2 ? d_basic : (const float *) nullptr,
            ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
@@ -858,12 +871,12 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
         for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
     }
     // (the accumulators were cropped back after every core call)
-    for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) touched[win.st[a]] = 1;
+    for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) S.touched[win.st[a]] = 1;
     ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
     ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
-    remaining = 0;
-    for (unsigned st = 0; st < asize; st++) remaining += proc[st] == 0;
-    passes++;
+    S.remaining = 0;
+    for (unsigned st = 0; st < asize; st++) S.remaining += proc[st] == 0;
+    S.passes++;
     return 0;
 }
 
@@ -873,22 +886,9 @@ int step_end(lfbm5d_ctx *ctx, float *d_out)
     const lfbm5d_params *p = &S.p;
     const int step = S.step;
     float *d_noisy = S.d_noisy, *d_basic = S.d_basic;
-    const std::vector<unsigned> &mask = S.mask;
-    std::vector<unsigned> &proc = S.proc;
-    std::vector<char> &touched = S.touched;
-    unsigned &remaining = S.remaining, &tau_4D = S.tau_4D, &tables_tau4 = S.tables_tau4, &passes = S.passes;
-    const unsigned max_proc = S.max_proc;
-    PassCfg &pc = S.pc;
+    const unsigned asize = S.asize(), C = p->chnls;
+    const size_t HW = (size_t) p->width * p->height;
     const bool docolor = S.docolor;
-    const unsigned asize = p->awidth * p->aheight, asw = 2 * p->an + 1, Aw = asw * asw;
-    const unsigned cs = p->aheight / 2, ct = p->awidth / 2;
-    const unsigned cst = p->ang_major == LFBM5D_ROWMAJOR ? cs * p->awidth + ct : cs + ct * p->aheight;
-    const unsigned C = p->chnls, W = p->width, H = p->height;
-    const size_t HW = (size_t) W * H, each = HW * C;
-    unsigned long long *counters = ctx->counters.as<unsigned long long>();
-    (void) step; (void) d_noisy; (void) d_basic; (void) mask; (void) proc; (void) touched; (void) remaining; (void) tau_4D; (void) tables_tau4;
-    (void) passes; (void) max_proc; (void) pc; (void) docolor; (void) asize; (void) asw; (void) Aw; (void) cs; (void) ct; (void) cst; (void) C; (void) W;
-    (void) H; (void) HW; (void) each; (void) counters;
     LAUNCH(ctx, k_final, grid_for(ctx, asize * HW), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), d_noisy, d_basic, d_out,
            ctx->mask.as<unsigned>(), asize, HW, (int) C, step, p->color_space, docolor ? 1 : 0);
     CK(cudaGetLastError());
@@ -948,6 +948,7 @@ int validate_bm3d(const lfbm3d_params *p)
     if (p->nHard + 1 < std::max(p->kHard, p->kWien)) return fail("nHard must be >= k - 1");
     if (p->color_space > LFBM5D_RGB) return fail("Wrong type of transform. Must be OPP, YUV, or YCbCr!!");
     if (p->width < 16 || p->height < 16) return fail("image smaller than a patch");
+    if (p->width < p->nHard || p->height < p->nHard) return fail("image smaller than the padding nHard");
     return 0;
 }
 
@@ -1180,6 +1181,13 @@ int lfbm5d_step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt)
     return step_window(ctx, ps, pt);
 }
 
+int lfbm5d_step_window_ex(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, int sadct)
+{
+    if (!ctx || !ctx->ss.active) return fail("no step in progress");
+    if (ps >= ctx->ss.p.aheight || pt >= ctx->ss.p.awidth) return fail("SAI index out of range");
+    return step_window(ctx, ps, pt, sadct ? 1 : 0);
+}
+
 int lfbm5d_step_end(lfbm5d_ctx *ctx, float *d_out)
 {
     if (!ctx || !ctx->ss.active || !d_out) return fail("no step in progress");
@@ -1324,6 +1332,54 @@ int lfbm5d_debug_pass_ex(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, cons
         std::vector<unsigned char> s(pc.A * plane);
         CK(cudaMemcpy(s.data(), ctx->shape.p, pc.A * plane, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < s.size(); i++) out_shape[i] = s[i];
+    }
+    return 0;
+}
+
+
+int lfbm5d_debug_block_matching(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, const float *planes, unsigned nplanes,
+                                unsigned *out_count, unsigned *out_idx, unsigned *out_first, unsigned *out_shape)
+{
+    if (!ctx || !p || !planes) return fail("null argument");
+    if (step != 1 && step != 2) return fail("step must be 1 or 2");
+    lfbm5d_params q = *p;
+    if (q.awidth < 2 * q.an + 1) q.awidth = 2 * q.an + 1;
+    if (q.aheight < 2 * q.an + 1) q.aheight = 2 * q.an + 1;
+    if (validate(&q, step)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    PassCfg pc;
+    if (make_passcfg(pc, step, p, p->tau_4D) || setup_tables(ctx, step, p, p->tau_4D) || ensure_pass_buffers(ctx, pc) || upload_grid(ctx, pc))
+        return 1;
+    if (nplanes < 1 || nplanes > pc.A) return fail("1 <= nplanes <= (2*an+1)^2");
+    const size_t plane = (size_t) pc.wb * pc.hb;
+    LfWindow win{};
+    win.A = (int) pc.A;
+    for (unsigned a = 0; a < pc.A; a++) { win.st[a] = (int) a; win.mask[a] = a < nplanes; win.proc[a] = a >= nplanes; }
+    CK(cudaMemcpyAsync(ctx->est0.p, planes, nplanes * plane * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->first.p, 0xFF, pc.A * plane * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->shape.p, 0, pc.A * plane, ctx->stream));
+    ctx->bm_only = true;
+    const int rc = run_pass(ctx, pc, win, 0, 0);
+    ctx->bm_only = false;
+    if (rc) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t R = pc.rows.size() * pc.cols.size(), nc = pc.cols.size();
+    if (out_count && out_idx) {
+        std::vector<unsigned> cnt(R), idx(R * (pc.N + 1));
+        CK(cudaMemcpy(cnt.data(), ctx->bmcount.p, R * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(idx.data(), ctx->bmidx.p, R * (pc.N + 1) * 4, cudaMemcpyDeviceToHost));
+        memset(out_count, 0, plane * 4);
+        for (size_t r = 0; r < R; r++) {
+            const size_t k_r = (size_t) pc.rows[r / nc] * pc.wb + pc.cols[r % nc];
+            out_count[k_r] = cnt[r];
+            for (unsigned n = 0; n < cnt[r]; n++) out_idx[k_r * (pc.N + 1) + n] = idx[r * (pc.N + 1) + n];
+        }
+    }
+    if (out_first) CK(cudaMemcpy(out_first, ctx->first.p, nplanes * plane * 4, cudaMemcpyDeviceToHost));
+    if (out_shape) {
+        std::vector<unsigned char> sh(nplanes * plane);
+        CK(cudaMemcpy(sh.data(), ctx->shape.p, nplanes * plane, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < sh.size(); i++) out_shape[i] = sh[i];
     }
     return 0;
 }

@@ -1,6 +1,8 @@
 // See lfbm5d_host.h. Error behaviour follows the reference's drivers: message on cout, EXIT_FAILURE (1).
 #include "lfbm5d_host.h"
 #include "lfbm5d_cuda.h"
+#include "lfbm5d_host_c.h"
+#include "lf_io.h"
 #include <cstdlib>
 #include <iostream>
 
@@ -116,3 +118,27 @@ int run_bm3d_LF(const float sigma, std::vector<std::vector<float> > &LF_noisy, s
     }
     return EXIT_SUCCESS;
 }
+
+// ---- C exports of the host-side noise / metric helpers of the command lines (include/lfbm5d_host_c.h) ----
+extern "C" {
+
+void lfio_add_noise(const float *img, float *out, size_t n, float sigma, unsigned long seed)
+{
+    lfio::MT g;
+    g.seed(seed);
+    for (size_t k = 0; k < n; k++) {      // utilities.cpp:177-184
+        const double a = g.res53(), b = g.res53();
+        const double z = (double) sigma * sqrt(-2.0 * log(a)) * cos(2.0 * M_PI * b);
+        out[k] = img[k] + (float) z;
+    }
+}
+
+void lfio_psnr(const float *a, const float *b, size_t n, float *psnr, float *rmse)
+{
+    float tmp = 0.0f;      // utilities.cpp:427-432: float accumulator
+    for (size_t k = 0; k < n; k++) tmp += (a[k] - b[k]) * (a[k] - b[k]);
+    *rmse = sqrtf(tmp / (float) n);
+    *psnr = 20.0f * log10f(255.0f / (*rmse));
+}
+
+} // extern "C"

@@ -124,9 +124,8 @@ def run_step_windows(eng, step, prm, d_noisy, d_basic, mask, d_out, dist, device
         owners = window_owner(wins, world)
         for w, o in zip(wins, owners):
             if o == rank:
-                if int(w[5]):
-                    eng.step_force_sadct()
-                eng.step_window(int(w[0]), int(w[1]))
+                # the dct -> sadct switch comes from the plan entry: list scheduling runs windows out of their sequential order
+                eng.step_window(int(w[0]), int(w[1]), sadct=int(w[5]))
         eng.step_accumulators()                      # waits for this rank's windows (the library has its own stream)
         if world > 1:
             works = []

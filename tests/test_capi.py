@@ -24,6 +24,24 @@ def test_exports_match_header():
     assert sorted(L.EXPORTS) == syms
 
 
+def test_host_library_exports_and_noise(oracle):
+    """include/lfbm5d_host_c.h: every declared symbol is exported; the product's mt19937ar noise and PSNR equal the oracle's
+    restatement of utilities.cpp:154-185 / :412-435 (itself pinned to the reference) bit for bit."""
+    import numpy as np
+    import lfbm5d_b200 as L
+    src = open(os.path.join(ROOT, "include", "lfbm5d_host_c.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(lfio_[a-z0-9_]+)\s*\(", src)))
+    h = L.load_host_library()
+    assert syms == sorted(L.HOST_EXPORTS)
+    for s in syms:
+        assert hasattr(h, s), "missing export " + s
+    clean = np.random.RandomState(3).rand(4, 3, 20, 24).astype(np.float32) * 255
+    a, b = L.add_noise(clean, 25.0), oracle.add_noise(clean, 25.0)
+    assert np.array_equal(a, b)
+    assert L.psnr(a, clean) == oracle.psnr(a, clean)
+
+
 def test_params_struct_layout():
     import lfbm5d_b200 as L
     assert C.sizeof(L.Params) == 20 * 4

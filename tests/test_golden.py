@@ -84,3 +84,23 @@ def test_schedule_pass_counts(oracle):
     b, nrt, sch = oracle.run_step1(noisy, np.ones(81), 10.0, 2.7, 9, 9, 1, 2, 2, 1, 8, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
     assert len(sch) == 16 and int(sch[0][0]) == 40 and int(sch[1][0]) == 80
     assert sorted(set(int(e[0]) for e in sch)) == sorted(int(e[0]) for e in sch)
+
+
+def test_config1_fixture_golden(oracle):
+    """BASELINE.json configs[0] (the reference's fixture, README.md:50 parameters): the oracle reproduces the unmodified reference's
+    basic and denoised estimates bit for bit (tiles + PSNRs of tests/golden/config1.npz, tests/make_golden_config1.py)."""
+    g = np.load(os.path.join(GOLD, "config1.npz"))
+    clean = g["clean_u8"].astype(np.float32)
+    noisy = oracle.add_noise(clean, 25.0)
+    mask = np.ones(9)
+    b, nrt, sched = oracle.run_step1(noisy, mask, 25.0, 2.7, 3, 3, 1, 8, 18, 6, 16, 4, oracle.ID, oracle.SADCT, oracle.HAAR)
+    d, _, _, _ = oracle.run_step2(nrt, b, mask, 25.0, 3, 3, 1, 16, 18, 6, 8, 4, oracle.DCT, oracle.SADCT, oracle.HAAR)
+    assert len(sched) == 1
+    sais = [0, 4, 8]
+    tiles = {"centre": (slice(96, 160), slice(96, 160)), "corner": (slice(0, 40), slice(0, 40)), "edge": (slice(216, 256), slice(100, 164))}
+    for name, (ys, xs) in tiles.items():
+        assert np.array_equal(b[sais][:, :, ys, xs], g["basic_" + name]), name
+        assert np.array_equal(d[sais][:, :, ys, xs], g["denoised_" + name]), name
+    assert oracle.psnr(b, clean)[0] == float(g["psnr_basic"]) and oracle.psnr(d, clean)[0] == float(g["psnr_denoised"])
+    # the reference's own sensitivity to the unpinned FFTW arithmetic (double-accumulating stand-in): the noise floor of dPSNR
+    assert abs(float(g["psnr_denoised_f64dct"]) - float(g["psnr_denoised"])) < 0.01
