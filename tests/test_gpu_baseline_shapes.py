@@ -102,6 +102,20 @@ def test_pass_config1_shape_and_wide_plane(eng, oracle):
         check_pass(eng, oracle, 2, sym, basic, z, z, mask, proc, 8, 16, oracle.DCT, oracle.SADCT, oracle.HAAR, sigma=sigma, lam=0.0)
 
 
+def test_pass_full_size_window(eng, oracle):
+    """One teacher-forced window pass per step on 3x3 SAIs of 1024^2 (configs[2] / configs[3] SAI size; 9 x 3 planes of 1072^2,
+    64,009 / 65,025 groups): match tables and step-1 accumulators bit-exact, step 2 within 2e-5 relative."""
+    import golden_inputs as gi
+    _, _, sym = gi.pad_inputs(1024, 1024, 10.0)
+    z = np.zeros_like(sym)
+    mask, proc = np.ones(9, np.uint32), np.zeros(9, np.uint32)
+    on, od, gn, gd = check_pass(eng, oracle, 1, sym, None, z, z, mask, proc, 16, 8, oracle.ID, oracle.SADCT, oracle.HAAR, sigma=10.0)
+    assert np.array_equal(gn, on) and np.array_equal(gd, od)
+    basic = estimate(on, od, sym)
+    del on, od, gn, gd
+    check_pass(eng, oracle, 2, sym, basic, z, z, mask, proc, 8, 16, oracle.DCT, oracle.SADCT, oracle.HAAR, sigma=10.0, lam=0.0)
+
+
 def test_config1_fixture_against_reference(eng, oracle):
     """BASELINE.json configs[0]: the reference's fixture testing/sourceLF with mt19937ar noise (seed 20171016 + st), README.md:50
     parameters, through the host-buffer entry points; against tiles and PSNRs produced by the unmodified reference
