@@ -112,6 +112,28 @@ unsigned lfbm5d_step_plan(const lfbm5d_params *p, const unsigned *sai_mask, unsi
 /* a window with an empty SAI earlier in the sequential order turns tau_4D = dct into sadct for the rest of the step (bm5d.cpp:276-280) */
 int lfbm5d_step_force_sadct(lfbm5d_ctx *ctx);
 
+/* ---- one light field on several GPUs: a team of ranks that split every window pass (lfbm5d_b200/csrc/team.cuh) ----
+ * Reference rows of the pass grid, and the pixel rows they aggregate into, are dealt out in bands (north_star's row-band partition,
+ * halo = search radius + patch size); the offset planes of the block matching are dealt out whole. Results are bit-identical to the
+ * single-GPU entry points. One process per GPU: every rank creates its context, rank 0 draws lfbm5d_team_unique_id and ships the
+ * 128 bytes to the others (e.g. torch.distributed / MPI broadcast), every rank calls lfbm5d_team_create_nccl (NCCL is loaded with
+ * dlopen at that point). lfbm5d_team_create_emulated puts `world` ranks as contexts on ONE device and replaces the exchanges by
+ * device copies (how the band logic is tested on a single GPU). */
+typedef struct lfbm5d_team lfbm5d_team;
+int  lfbm5d_team_create_emulated(lfbm5d_team **out, int device, int world);
+int  lfbm5d_team_unique_id(char *id128);
+int  lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int world, const char *id128);
+void lfbm5d_team_destroy(lfbm5d_team *team);
+int  lfbm5d_team_local_ranks(lfbm5d_team *team);      /* emulated: world; NCCL: 1 */
+/* One step (1 or 2) of ONE light field on the whole team. d_*: arrays of lfbm5d_team_local_ranks() device pointers, one replica of the
+ * light field per local rank ([asize][chnls][height][width] floats, as for lfbm5d_step{1,2}_device). A rank reads and colour-transforms
+ * only the rows of its band (+ halo) of d_noisy_io / d_basic_io; on return d_out[l] holds the rows [row_lo, keep_hi) of lfbm5d_team_band
+ * (d_basic_io of step 2 may be the d_out of step 1 as it is), or, with gather != 0, the complete result on every rank. */
+int  lfbm5d_team_step(lfbm5d_team *team, int step, const lfbm5d_params *p, float *const *d_noisy_io, float *const *d_basic_io,
+                      const unsigned *sai_mask, float *const *d_out, int gather);
+int  lfbm5d_team_band(lfbm5d_team *team, int rank, int *row_lo, int *row_hi, int *keep_hi);
+void lfbm5d_team_stats(lfbm5d_team *team, unsigned long long *bytes_exchanged, unsigned *passes_redone);
+
 /* ---- parity/debug exports (used by tests only) ---------------------------------------------------
  * One window pass (the reference's bm5d_1st_step / bm5d_2nd_step, `pst == cst` branch) on HOST padded
  * buffers [A][chnls][h_b][w_b], A = (2*an+1)^2, h_b = height + 2*(nSim+nDisp); p->width/height are the

@@ -45,7 +45,9 @@ EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset
            "lfbm5d_enable_timing", "lfbm5d_stream", "lfbm5d_step1", "lfbm5d_step2", "lfbm3d_run", "lfbm5d_step1_device",
            "lfbm5d_step2_device", "lfbm3d_run_device", "lfbm5d_set_max_passes", "lfbm5d_debug_pass", "lfbm5d_debug_pass_ex",
            "lfbm5d_debug_schedule", "lfbm5d_step_begin", "lfbm5d_step_window", "lfbm5d_step_end", "lfbm5d_step_accumulators",
-           "lfbm5d_step_plan", "lfbm5d_step_force_sadct", "lfbm5d_step_window_ex", "lfbm5d_debug_block_matching"]
+           "lfbm5d_step_plan", "lfbm5d_step_force_sadct", "lfbm5d_step_window_ex", "lfbm5d_debug_block_matching", "lfbm5d_team_create_emulated", "lfbm5d_team_unique_id",
+           "lfbm5d_team_create_nccl", "lfbm5d_team_destroy", "lfbm5d_team_local_ranks", "lfbm5d_team_step", "lfbm5d_team_band",
+           "lfbm5d_team_stats"]
 
 HOST_LIB_PATH = os.path.join(_HERE, "_lib", "liblfbm5d_host.so")
 HOST_EXPORTS = ["lfio_add_noise", "lfio_psnr"]           # include/lfbm5d_host_c.h
@@ -291,3 +293,73 @@ class LFBM5D(object):
         if rc != 0:
             raise RuntimeError("lfbm5d_debug_pass: " + self.error())
         return (num, den, dbg) if debug else (num, den)
+
+
+class Team(object):
+    """One light field on several GPUs: the ranks of a team split every window pass (include/lfbm5d_cuda.h, csrc/team.cuh).
+    Team.nccl: one process per GPU (this process is rank `rank`); Team.emulated: `world` ranks on ONE device (tests)."""
+
+    def __init__(self, handle, engine=None):
+        self.lib = load_library()
+        self.handle = handle
+        self.engine = engine          # keeps the context of an NCCL team alive
+
+    @classmethod
+    def emulated(cls, device, world):
+        lib = load_library()
+        h = C.c_void_p()
+        if lib.lfbm5d_team_create_emulated(C.byref(h), int(device), int(world)) != 0:
+            raise RuntimeError("lfbm5d_team_create_emulated: " + lib.lfbm5d_last_error().decode())
+        return cls(h)
+
+    @staticmethod
+    def unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        if lib.lfbm5d_team_unique_id(buf) != 0:
+            raise RuntimeError("lfbm5d_team_unique_id: " + lib.lfbm5d_last_error().decode())
+        return buf.raw
+
+    @classmethod
+    def nccl(cls, engine, rank, world, unique_id):
+        lib = load_library()
+        h = C.c_void_p()
+        if lib.lfbm5d_team_create_nccl(C.byref(h), engine.ctx, int(rank), int(world), C.c_char_p(bytes(unique_id))) != 0:
+            raise RuntimeError("lfbm5d_team_create_nccl: " + lib.lfbm5d_last_error().decode())
+        return cls(h, engine)
+
+    def close(self):
+        if self.handle:
+            self.lib.lfbm5d_team_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def local_ranks(self):
+        return int(self.lib.lfbm5d_team_local_ranks(self.handle))
+
+    def step(self, step, prm, d_noisy, d_basic, mask, d_out, gather=0):
+        """d_noisy / d_basic / d_out: lists of device pointers, one per local rank (d_basic ignored for step 1)."""
+        n = self.local_ranks()
+        arr = lambda ptrs: (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in ptrs])
+        m = np.ascontiguousarray(mask, np.uint32)
+        rc = self.lib.lfbm5d_team_step(self.handle, int(step), C.byref(prm), arr(d_noisy), arr(d_basic) if int(step) == 2 else None, _up(m),
+                                       arr(d_out), int(gather))
+        if rc != 0:
+            raise RuntimeError("lfbm5d_team_step: " + self.lib.lfbm5d_last_error().decode())
+
+    def band(self, rank):
+        """(row_lo, row_hi, keep_hi): rank owns the interior rows [row_lo, row_hi) and holds valid results on [row_lo, keep_hi)."""
+        lo, hi, keep = C.c_int(), C.c_int(), C.c_int()
+        if self.lib.lfbm5d_team_band(self.handle, int(rank), C.byref(lo), C.byref(hi), C.byref(keep)) != 0:
+            raise RuntimeError("lfbm5d_team_band: " + self.lib.lfbm5d_last_error().decode())
+        return lo.value, hi.value, keep.value
+
+    def stats(self):
+        b, r = C.c_ulonglong(), C.c_uint()
+        self.lib.lfbm5d_team_stats(self.handle, C.byref(b), C.byref(r))
+        return {"bytes_exchanged": int(b.value), "passes_redone": int(r.value)}

@@ -8,6 +8,7 @@
 
 struct GroupArgs {
     int C, asw, A, k, log2k, N, w, h, pst, nc;
+    int r0;                           // first reference patch of the launch (blockIdx.x + r0; row bands of the multi-GPU path)
     int RS, PS;                       // shared-memory row stride / patch stride (floats)
     unsigned tau_2D, tau_4D, tau_5D;
     const int *rows, *cols;
@@ -511,11 +512,11 @@ __global__ void k_active_refs(const float *__restrict__ den0, const int *__restr
 }
 
 // bit st of gmask[r]: SAI st belongs to the angular shape of reference patch r (core:300-312)
-__global__ void k_group_masks(const int *__restrict__ rows, const int *__restrict__ cols, int nc, int R, int w, unsigned plane, int A, int pst,
+__global__ void k_group_masks(const int *__restrict__ rows, const int *__restrict__ cols, int nc, int r0, int r1, int w, unsigned plane, int A, int pst,
                               LfWindow win, const unsigned char *__restrict__ shape, unsigned short *__restrict__ gmask)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
+    const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= r1) return;
     const int k_r = rows[r / nc] * w + cols[r % nc];
     unsigned m = 0;
     for (int st = 0; st < A; ++st) {
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(256) k_groups(GroupArgs g)
     __shared__ unsigned char szero[LF_MAXN * LF_MAXA];    // patch reads as zeros (empty SAI, or column w-k: core:1697)
     constexpr int A = ASW * ASW;
     const int tid = threadIdx.x;
-    const int r = blockIdx.x;
+    const int r = blockIdx.x + g.r0;
     const int k = g.k, k2 = k * k, w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int nSx = (int) g.bm_count[r];
@@ -811,7 +812,7 @@ __global__ void __launch_bounds__(256) k_groups_id16(GroupArgs g, unsigned long 
     __shared__ __align__(16) unsigned sofs[8 * 9];
     constexpr int A = 9, k = 16, k2 = 256;
     const int tid = threadIdx.x;
-    const int r = blockIdx.x;
+    const int r = blockIdx.x + g.r0;
     const int w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int nSx = (int) g.bm_count[r];
@@ -849,6 +850,8 @@ struct AggArgs {
     const float *zbuf, *wbuf;
     float *numsym, *densym;
     const int *arange, *brange;    // per tile row / tile column: first and last candidate reference row / column index
+    int y_lo, y_hi;                // pixel rows of this launch; reference rows a_min..a_max only (row bands of the multi-GPU path)
+    int a_min, a_max, ty0;         // ty0: first tile row of the grid
     LfWindow win;
 };
 #define AGG_CAP_K8 1024     // list capacity for k = 8 (more, smaller patches per tile: one flush per tile) ...
@@ -868,15 +871,16 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
     if (!g.win.mask[st] || g.win.proc[st]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = K ? K : g.k, k2 = k * k, A = g.A, C = CC ? CC : g.C, N = g.N;
-    const int y0 = blockIdx.y * 16, x0 = blockIdx.x * 16;
+    const int tyb = blockIdx.y + g.ty0;
+    const int y0 = tyb * 16, x0 = blockIdx.x * 16;
     // a warp owns an 8 (x) by 4 (y) block of the tile: the squarer the footprint, the fewer patches touch it and the more
     // of its lanes each of them covers
     const int wy0 = y0 + (warp >> 1) * 4, wx0 = x0 + (warp & 1) * 8;
     const int y = wy0 + (lane >> 3), x = wx0 + (lane & 7);
-    const bool inimg = y < g.h && x < g.w;
+    const bool inimg = y < g.y_hi && y >= g.y_lo && x < g.w;
     const size_t plane = (size_t) g.w * g.h;
     for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
-    const int a_lo = g.arange[2 * blockIdx.y], a_hi = g.arange[2 * blockIdx.y + 1];
+    const int a_lo = max(g.arange[2 * tyb], g.a_min), a_hi = min(g.arange[2 * tyb + 1], g.a_max);
     const int b_lo = g.brange[2 * blockIdx.x], b_hi = g.brange[2 * blockIdx.x + 1];
     const int nbn = (b_hi - b_lo + 1) * N;                 // candidates per reference row: (column, n)
     float num[3] = { 0.f, 0.f, 0.f }, den[3] = { 0.f, 0.f, 0.f };

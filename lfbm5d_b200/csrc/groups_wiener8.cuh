@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(W8_NT, 2) k_groups_w8(GroupArgs g, unsigned lo
     constexpr int A = 9, K2 = 64;
     const int C = CC ? CC : g.C;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int r = blockIdx.x;
+    const int r = blockIdx.x + g.r0;
     const int w = g.w;
     const unsigned plane = (unsigned) g.w * (unsigned) g.h;
     const int nSx = (int) g.bm_count[r];

@@ -16,6 +16,7 @@
 #include <vector>
 #include <algorithm>
 #include <mutex>
+#include <memory>
 
 namespace {
 
@@ -111,6 +112,20 @@ struct PassCfg {
     std::vector<int> rows, cols;
 };
 
+
+// Host description of the offset planes of a pass: depends only on pst, the window mask, the (partial) extents and the buffers.
+struct SatPlan {
+    std::vector<SatPlane> planes;
+    std::vector<SatGroup> groups;
+    std::vector<int> stereo_sai;        // window slot of every stereo slot
+    int nself_groups = 0, nself_planes = 0, nslots = 0, groups_per_slot = 0;
+    int st_lo = 0, st_row_end = 0, st_col_end = 0, st_strips = 0, st_SR = 0;
+    size_t st_stride = 0;
+    int self_row_end = 0, self_col_end = 0, self_strips = 0, pstrips = 1;
+    DevBuf d_planes, d_groups;
+    std::vector<size_t> key;
+};
+
 } // namespace
 
 // state of a step between step_begin and step_end
@@ -155,6 +170,7 @@ struct lfbm5d_ctx {
     std::vector<unsigned> sched;
     bool geom_valid = false;
     unsigned geom_key[8]{};
+    std::vector<std::unique_ptr<SatPlan>> sat_cache;     // plane tables per window shape (sat_plan)
     LfTables tab;                 // this context's constants; c_tab (one per device) is reloaded when it holds another context's
 };
 
@@ -362,8 +378,7 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
     if (ctx->bmcount.ensure(R * 4) || ctx->bmidx.ensure(R * (pc.N + 1) * 4)) return 1;
     const size_t nplanes = nself + (pc.A - 1) * Nd * Nd;
     const size_t max_strips = std::max(st_strips, (size_t) (pc.wb - 2 * pc.n + 31) / 32);
-    if (ctx->satplanes.ensure(nplanes * sizeof(SatPlane)) || ctx->satgroups.ensure(nplanes * sizeof(SatGroup)) ||
-        ctx->bnd.ensure(nplanes * max_strips * pc.hb * 4) || ctx->progress.ensure((nplanes * max_strips + 4) * 4)) return 1;
+    if (ctx->bnd.ensure(nplanes * max_strips * pc.hb * 4) || ctx->progress.ensure((nplanes * max_strips + 4) * 4)) return 1;
     if (ctx->counters.ensure(64 * 8)) return 1;
     if (ctx->zbuf.ensure(R * pc.N * pc.A * pc.C * pc.k * pc.k * 4) || ctx->wbuf.ensure(R * pc.C * 4) ||
         ctx->spos.ensure(R * pc.N * pc.A * 4)) return 1;
@@ -412,204 +427,226 @@ int ensure_shape_lut(lfbm5d_ctx *ctx, unsigned asw)
     return 0;
 }
 
-// One core call on the padded device buffers of the window (nsym/bsym/numsym/densym/est0 already filled).
-// cst = slot the window was centred on: pst != cst is the partial-window branch (core:531-821 / :1332-1658).
-int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, int cst = -1)
-{
-    const bool partial = cst >= 0 && cst != pst;
-    if (ensure_tables(ctx)) return 1;
-    int act_ymax = -1, act_xmax = -1;       // partial-window branch: last row / column of a reference patch that is still processed
-    if (partial) {
-        const size_t Rr = pc.rows.size() * pc.cols.size();
-        if (ctx->act.ensure(Rr + 16)) return 1;
-        unsigned *cnt = reinterpret_cast<unsigned *>(ctx->act.as<unsigned char>() + ((Rr + 3) & ~(size_t) 3));
-        CK(cudaMemsetAsync(cnt, 0, 12, ctx->stream));
-        LAUNCH(ctx, k_active_refs, (unsigned) ((Rr + 255) / 256), 256, 0,
-               ctx->densym.as<float>() + (size_t) pst * pc.C * pc.wb * pc.hb, ctx->rows.as<int>(), ctx->cols.as<int>(), (int) pc.cols.size(), (int) Rr,
-               (int) pc.wb, (int) pc.k, ctx->act.as<unsigned char>(), cnt);
-        unsigned h3[3] = { 0, 0, 0 };
-        CK(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (h3[0] == 0) return 0;       // nothing left to denoise in this SAI (core:160-165)
-        act_ymax = (int) h3[1]; act_xmax = (int) h3[2];
-    }
-    const size_t plane = (size_t) pc.wb * pc.hb;
-    const int nr = (int) pc.rows.size(), nc = (int) pc.cols.size(), R = nr * nc;
-    const int Ns = 2 * (int) pc.nSim + 1, nself = pc.N > 1 ? ((int) pc.nSim + 1) * Ns : 0;
-    const int Nd = 2 * (int) pc.nDisp + 1, nd2 = Nd * Nd;
-    const float threshold = pc.tauMatch * pc.k * pc.k;       // core:3315
-    const float *est0 = ctx->est0.as<float>();
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+// ---- one core call, in pieces: the single-GPU run_pass strings them together; the multi-GPU team path (team.cuh) runs them
+// band by band with exchanges in between ----
 
-    // ---- offset planes: groups of <= 13 planes sharing their source rows (same images, same row offset) ----
-    std::vector<SatPlane> planes;
-    std::vector<SatGroup> groups;
-    std::vector<int> stereo_sai;
-    const float *ref0 = est0 + (size_t) pst * plane;
-    for (int di = 0; di < (nself ? (int) pc.nSim + 1 : 0); di++)
+struct PassGeom {      // derived sizes of a pass
+    size_t plane;
+    int nr, nc, R, Ns, nself, Nd, nd2;
+    float threshold;
+};
+PassGeom pass_geom(const PassCfg &pc)
+{
+    PassGeom g;
+    g.plane = (size_t) pc.wb * pc.hb;
+    g.nr = (int) pc.rows.size(); g.nc = (int) pc.cols.size(); g.R = g.nr * g.nc;
+    g.Ns = 2 * (int) pc.nSim + 1; g.nself = pc.N > 1 ? ((int) pc.nSim + 1) * g.Ns : 0;
+    g.Nd = 2 * (int) pc.nDisp + 1; g.nd2 = g.Nd * g.Nd;
+    g.threshold = pc.tauMatch * pc.k * pc.k;       // core:3315
+    return g;
+}
+
+// Plane tables of a pass, cached per (pst, window mask, extents, buffers): the same few windows shapes recur in every step.
+SatPlan *sat_plan(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, bool partial, int act_ymax, int act_xmax)
+{
+    const PassGeom pg = pass_geom(pc);
+    unsigned maskbits = 0;
+    for (int st = 0; st < (int) pc.A; st++) maskbits |= (win.mask[st] ? 1u : 0u) << st;
+    std::vector<size_t> key = { (size_t) pst, (size_t) maskbits, (size_t) partial, (size_t) (act_ymax + 1), (size_t) (act_xmax + 1),
+                                (size_t) pc.wb, (size_t) pc.hb, (size_t) pc.k, (size_t) pc.nSim, (size_t) pc.nDisp, (size_t) pc.N, (size_t) pc.A,
+                                (size_t) pg.R, (size_t) ctx->est0.p, (size_t) ctx->s_at.p, (size_t) ctx->s_mir.p, (size_t) ctx->sums.p };
+    for (auto &e : ctx->sat_cache) if (e->key == key) return e.get();
+    if (ctx->sat_cache.size() >= 48) {      // bounded: drop everything (the in-flight kernels read the tables: wait for them)
+        cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream3);
+        for (auto &e : ctx->sat_cache) { e->d_planes.release(); e->d_groups.release(); }
+        ctx->sat_cache.clear();
+    }
+    std::unique_ptr<SatPlan> sp(new SatPlan());
+    SatPlan &P = *sp;
+    P.key = key;
+    const float *est0 = ctx->est0.as<float>();
+    const float *ref0 = est0 + (size_t) pst * pg.plane;
+    const int Ns = pg.Ns, Nd = pg.Nd, R = pg.R;
+    // ---- offset planes: groups of <= 14 planes sharing their source rows (same images, same row offset) ----
+    for (int di = 0; di < (pg.nself ? (int) pc.nSim + 1 : 0); di++)
         for (int djx0 = 0; djx0 < Ns; djx0 += 2 * SAT_NW) {
             SatGroup G{};
             G.img1 = ref0; G.img2 = ref0; G.oy = di; G.oxmin = djx0 - (int) pc.nSim;      // core:3331: dk = di*w + djx - nSim
-            G.first_plane = (int) planes.size();
+            G.first_plane = (int) P.planes.size();
             for (int djx = djx0; djx < std::min(Ns, djx0 + 2 * SAT_NW); djx++) {
-                SatPlane P{};
+                SatPlane Q{};
                 const int ddk = di * Ns + djx;
-                P.ox = djx - (int) pc.nSim;
-                P.out_at = ctx->s_at.as<float>() + (size_t) ddk * R;
-                P.out_mir = ctx->s_mir.as<float>() + (size_t) ddk * R;
-                P.mir_di = di; P.mir_dc = (int) pc.nSim - djx;
-                planes.push_back(P);
+                Q.ox = djx - (int) pc.nSim;
+                Q.out_at = ctx->s_at.as<float>() + (size_t) ddk * R;
+                Q.out_mir = ctx->s_mir.as<float>() + (size_t) ddk * R;
+                Q.mir_di = di; Q.mir_dc = (int) pc.nSim - djx;
+                P.planes.push_back(Q);
                 G.nplanes++;
             }
-            groups.push_back(G);
+            P.groups.push_back(G);
         }
-    const int nself_groups = (int) groups.size(), nself_planes = (int) planes.size();
+    P.nself_groups = (int) P.groups.size(); P.nself_planes = (int) P.planes.size();
     // The summed-area recurrences run from the top-left corner, so stopping them early changes nothing in what was computed.
     // The partial-window branch needs the self sums up to the last active reference patch (+ nSim columns for the mirrored
     // offsets) and the disparity results up to nSim rows / columns further (positions of the self matches); the reference
     // computes the whole planes there as well (core:3631-3788, :3806-3945) and reads the same values.
-    const int st_lo = pc.nDisp, st_row_full = pc.hb - pc.nDisp - pc.k + 1, st_col_full = pc.wb - pc.nDisp - pc.k + 1;
-    const int st_row_end = partial ? std::min(st_row_full, act_ymax + (int) pc.nSim + 1) : st_row_full;
-    const int st_col_end = partial ? std::min(st_col_full, act_xmax + (int) pc.nSim + 1) : st_col_full;
-    const int st_strips = (st_col_end - st_lo + 31) / 32, st_SR = (st_row_end - st_lo) + 31;
-    const size_t st_stride = (size_t) ((st_col_full - st_lo + 31) / 32) * ((st_row_full - st_lo) + 31) * 32;      // allocation: full planes
+    const int st_row_full = pc.hb - pc.nDisp - pc.k + 1, st_col_full = pc.wb - pc.nDisp - pc.k + 1;
+    P.st_lo = pc.nDisp;
+    P.st_row_end = partial ? std::min(st_row_full, act_ymax + (int) pc.nSim + 1) : st_row_full;
+    P.st_col_end = partial ? std::min(st_col_full, act_xmax + (int) pc.nSim + 1) : st_col_full;
+    P.st_strips = (P.st_col_end - P.st_lo + 31) / 32; P.st_SR = (P.st_row_end - P.st_lo) + 31;
+    P.st_stride = (size_t) ((st_col_full - P.st_lo + 31) / 32) * ((st_row_full - P.st_lo) + 31) * 32;      // allocation: full planes
+    P.groups_per_slot = Nd;
     int slot = 0;
     for (int st = 0; st < (int) pc.A; st++) {
         if (st == pst || !win.mask[st]) continue;
         for (int di = 0; di < Nd; di++) {      // core:3516: dk = (di - nDisp)*w + (dj - nDisp)
             SatGroup G{};
-            G.img1 = ref0; G.img2 = est0 + (size_t) st * plane; G.oy = di - (int) pc.nDisp; G.oxmin = -(int) pc.nDisp;
-            G.first_plane = (int) planes.size();
+            G.img1 = ref0; G.img2 = est0 + (size_t) st * pg.plane; G.oy = di - (int) pc.nDisp; G.oxmin = -(int) pc.nDisp;
+            G.first_plane = (int) P.planes.size();
             for (int dj = 0; dj < Nd; dj++) {
-                SatPlane P{};
-                P.ox = dj - (int) pc.nDisp;
-                P.out_skew = ctx->sums.as<float>() + ((size_t) slot * nd2 + (size_t) di * Nd + dj) * st_stride;
-                planes.push_back(P);
+                SatPlane Q{};
+                Q.ox = dj - (int) pc.nDisp;
+                Q.out_skew = ctx->sums.as<float>() + ((size_t) slot * pg.nd2 + (size_t) di * Nd + dj) * P.st_stride;
+                P.planes.push_back(Q);
                 G.nplanes++;
             }
-            groups.push_back(G);
+            P.groups.push_back(G);
         }
-        stereo_sai.push_back(st);
+        P.stereo_sai.push_back(st);
         slot++;
     }
-    if (!planes.empty()) {
-        CK(cudaMemcpyAsync(ctx->satplanes.p, planes.data(), planes.size() * sizeof(SatPlane), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->satgroups.p, groups.data(), groups.size() * sizeof(SatGroup), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const int self_row_end = partial ? std::min((int) pc.hb - (int) pc.n, act_ymax + 1) : (int) pc.hb - (int) pc.n;
-    const int self_col_end = partial ? std::min((int) pc.wb - (int) pc.n, act_xmax + (int) pc.nSim + 1) : (int) pc.wb - (int) pc.n;
-    const int self_strips = (self_col_end - (int) pc.n + 31) / 32;
-    int *ticket = ctx->progress.as<int>();      // [0]: self launch, [1]: stereo launch; flags follow
-    int *flags = ticket + 4;
+    P.nslots = slot;
+    P.self_row_end = partial ? std::min((int) pc.hb - (int) pc.n, act_ymax + 1) : (int) pc.hb - (int) pc.n;
+    P.self_col_end = partial ? std::min((int) pc.wb - (int) pc.n, act_xmax + (int) pc.nSim + 1) : (int) pc.wb - (int) pc.n;
+    P.self_strips = (P.self_col_end - (int) pc.n + 31) / 32;
     // one plane stride for both launches: they share bnd / progress and are told apart by their plane ids only
-    const int pstrips = std::max(std::max(self_strips, st_strips), 1);
-    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + planes.size() * (size_t) pstrips) * 4, ctx->stream));
-    cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
-    if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
-    // Self matching (summed-area planes, selection) stays on the main stream; disparity matching (planes, argmin, ties) runs
-    // beside it on a second stream: the issue-bound plane kernels overlap with the bandwidth-bound argmin and the latency-bound
-    // selection / tie kernels of the other branch. The two launches use disjoint plane indices of bnd / progress.
-    cudaStream_t sB = ctx->stream3;
-    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    CK(cudaStreamWaitEvent(sB, ctx->ev_fork, 0));
-    // the disparity planes are launched first: they finish first and their argmin then runs under the self planes
-    if (slot > 0) {
-        SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = st_lo; g.row_end = st_row_end; g.col_end = st_col_end;
-        g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = st_strips; g.pstrips = pstrips; g.SR = st_SR;
-        g.gp = 1; g.negzero2 = 0x8000000080000000ull;
-        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
-        const int ngroups = (int) groups.size() - nself_groups;
-        auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
-        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kfn<<<ngroups * st_strips, SAT_NW * 32, smem, sB>>>(g, ctx->satgroups.as<SatGroup>() + nself_groups,
-                                                            ctx->satplanes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
-        ctx->stats.kernel_launches++;
-    }
-    if (nself > 0) {
-        LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * threshold, (size_t) nself * R);   // core:3317
-        SatGeom g{};
-        g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = self_row_end; g.col_end = self_col_end;
-        g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = self_strips; g.pstrips = pstrips; g.SR = 0;
-        g.nc = nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
-        g.gp = pc.p; g.nr = nr; g.rlast = pc.rows.back();
-        g.nreg = 0;      // rows produced by the regular stride of ind_initialize (utilities.cpp:697-712)
-        for (unsigned ind = pc.n; ind < pc.hb - pc.k + 1 - pc.n; ind += pc.p) g.nreg++;
-        g.negzero2 = 0x8000000080000000ull;
-        const size_t smem = 2 * (128 + pc.k) * 64 * 4;
-        auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
-        CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        kfn<<<nself_groups * self_strips, SAT_NW * 32, smem, ctx->stream>>>(g, ctx->satgroups.as<SatGroup>(), ctx->satplanes.as<SatPlane>(),
-                                                                            nself_groups, ctx->bnd.as<float>(), flags, ticket);
-        ctx->stats.kernel_launches++;
-    }
-    (void) nself_planes;
-    if (ctx->timing) { CK(cudaEventRecord(sat1, ctx->stream)); CK(cudaEventRecord(ctx->ev_satb, sB)); }
-    // ---- selection ----
-    if (nself > 0) {
-        SelGeom sg{};
-        sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = Ns; sg.N = pc.N; sg.R = R; sg.nc = nc; sg.threshold = threshold;
-        sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
-        void (*kfast)(SelGeom, const float *, const float *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
-        switch (pc.N) {
-            case 2: kfast = k_bm_select_fast<3>; break;
-            case 4: kfast = k_bm_select_fast<5>; break;
-            case 8: kfast = k_bm_select_fast<9>; break;
-            case 16: kfast = k_bm_select_fast<17>; break;
-            case 32: kfast = k_bm_select_fast<33>; break;
-            default: break;
+    P.pstrips = std::max(std::max(P.self_strips, P.st_strips), 1);
+    if (!P.planes.empty()) {
+        if (P.d_planes.ensure(P.planes.size() * sizeof(SatPlane)) || P.d_groups.ensure(P.groups.size() * sizeof(SatGroup))) return nullptr;
+        // pageable source: the copies are staged before the calls return, the vectors stay alive in the cache anyway
+        if (cudaMemcpyAsync(P.d_planes.p, P.planes.data(), P.planes.size() * sizeof(SatPlane), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(P.d_groups.p, P.groups.data(), P.groups.size() * sizeof(SatGroup), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            fail("upload of the plane tables failed");
+            return nullptr;
         }
-        if (kfast) {
-            // one thread per reference patch; the few with an exact float tie among the selected distances go to the warp kernel
-            if (ctx->tielist.ensure((R + 1) * 4)) return 1;
-            unsigned *tl = ctx->tielist.as<unsigned>();
-            CK(cudaMemsetAsync(tl + R, 0, 4, ctx->stream));
-            LAUNCH(ctx, kfast, (R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(),
-                   ctx->bmidx.as<unsigned>(), tl, tl + R);
-            LAUNCH(ctx, k_bm_select, std::min<size_t>(R, (size_t) ctx->num_sms * 16), 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(),
-                   ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl, (const unsigned *) (tl + R));
-        } else
-            LAUNCH(ctx, k_bm_select, R, 32, (size_t) Ns * Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
-                   ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) nullptr, (const unsigned *) nullptr);
-    } else {
-        LAUNCH(ctx, k_bm_identity, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) pc.wb, R, (int) pc.N,
-               ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
     }
-    if (slot > 0) {
-        // every position could be tied (a flat light field): room for all of them
-        if (ctx->stielist.ensure(((size_t) slot * st_stride + 1) * 8)) return 1;
-        uint2 *sl = ctx->stielist.as<uint2>();
-        unsigned *sc = reinterpret_cast<unsigned *>(sl + (size_t) slot * st_stride);
-        CK(cudaMemsetAsync(sc, 0, 4, sB));
-        TieGeom tg{};
-        tg.plane_stride = st_stride; tg.w = (int) pc.wb; tg.nDisp = (int) pc.nDisp; tg.lo = st_lo; tg.nstrips = st_strips; tg.SR = st_SR;
-        tg.plane = (unsigned) plane;
-        for (int s = 0; s < slot; s++) {
-            const int st = stereo_sai[s];
-            tg.sai[s] = st;
-            LAUNCH_ON(ctx, sB, k_stereo_argmin, grid_for(ctx, st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * nd2 * st_stride, st_stride,
-                   (int) pc.wb, (int) pc.nDisp, st_lo, st_row_end, st_col_end, st_strips, st_SR, threshold,
-                   ctx->first.as<unsigned>() + (size_t) st * plane, ctx->shape.as<unsigned char>() + (size_t) st * plane, (unsigned) s, sl, sc);
-        }
-        const size_t smem_t = (size_t) 32 * LF_MAXNS2 * sizeof(LfPair);
-        CK(cudaFuncSetAttribute((const void *) k_stereo_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
-        LAUNCH_ON(ctx, sB, k_stereo_ties, ctx->num_sms * 4, 32, smem_t, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
-                  ctx->first.as<unsigned>());
-    }
-    CK(cudaEventRecord(ctx->ev_join, sB));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure(R * 2)) return 1;
-    LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), nc, (int) R, (int) pc.wb, (unsigned) plane,
-           (int) pc.A, (int) pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    if (ctx->bm_only) { CK(cudaGetLastError()); return 0; }
+    ctx->sat_cache.push_back(std::move(sp));
+    return ctx->sat_cache.back().get();
+}
 
-    // ---- groups ----
+// Summed-area planes of the self groups [sg0, sg1) on `strm` (ticket counter 0) ...
+int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg0, int sg1, cudaStream_t strm)
+{
+    if (sg1 <= sg0) return 0;
+    const PassGeom pg = pass_geom(pc);
+    int *ticket = ctx->progress.as<int>(), *flags = ticket + 4;
+    SatGeom g{};
+    g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = P.self_row_end; g.col_end = P.self_col_end;
+    g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = P.self_strips; g.pstrips = P.pstrips; g.SR = 0;
+    g.nc = pg.nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
+    g.gp = pc.p; g.nr = pg.nr; g.rlast = pc.rows.back();
+    g.nreg = 0;      // rows produced by the regular stride of ind_initialize (utilities.cpp:697-712)
+    for (unsigned ind = pc.n; ind < pc.hb - pc.k + 1 - pc.n; ind += pc.p) g.nreg++;
+    g.negzero2 = 0x8000000080000000ull;
+    const size_t smem = 2 * (128 + pc.k) * 64 * 4;
+    auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
+    CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kfn<<<(sg1 - sg0) * P.self_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), sg1 - sg0,
+                                                                  ctx->bnd.as<float>(), flags, ticket);
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+// ... and of the disparity slots [s0, s1) (ticket counter 1)
+int launch_sat_stereo(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int s0, int s1, cudaStream_t strm)
+{
+    if (s1 <= s0) return 0;
+    int *ticket = ctx->progress.as<int>(), *flags = ticket + 4;
+    SatGeom g{};
+    g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = P.st_lo; g.row_end = P.st_row_end; g.col_end = P.st_col_end;
+    g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = P.st_strips; g.pstrips = P.pstrips; g.SR = P.st_SR;
+    g.gp = 1; g.negzero2 = 0x8000000080000000ull;
+    const size_t smem = 2 * (128 + pc.k) * 64 * 4;
+    const int ngroups = (s1 - s0) * P.groups_per_slot;
+    auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
+    CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kfn<<<ngroups * P.st_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + P.nself_groups + s0 * P.groups_per_slot,
+                                                            P.d_planes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+
+// Selection of the self matches of every reference patch from the complete sampled sums (single GPU; team fallback under ties)
+int launch_self_select(lfbm5d_ctx *ctx, const PassCfg &pc, cudaStream_t strm)
+{
+    const PassGeom pg = pass_geom(pc);
+    const int R = pg.R;
+    SelGeom sg{};
+    sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = R; sg.nc = pg.nc; sg.threshold = pg.threshold;
+    sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
+    void (*kfast)(SelGeom, const float *, const float *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
+    switch (pc.N) {
+        case 2: kfast = k_bm_select_fast<3>; break;
+        case 4: kfast = k_bm_select_fast<5>; break;
+        case 8: kfast = k_bm_select_fast<9>; break;
+        case 16: kfast = k_bm_select_fast<17>; break;
+        case 32: kfast = k_bm_select_fast<33>; break;
+        default: break;
+    }
+    if (kfast) {
+        // one thread per reference patch; the few with an exact float tie among the selected distances go to the warp kernel
+        if (ctx->tielist.ensure((R + 1) * 4)) return 1;
+        unsigned *tl = ctx->tielist.as<unsigned>();
+        CK(cudaMemsetAsync(tl + R, 0, 4, strm));
+        LAUNCH_ON(ctx, strm, kfast, (R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(),
+                  ctx->bmidx.as<unsigned>(), tl, tl + R);
+        LAUNCH_ON(ctx, strm, k_bm_select, std::min<size_t>(R, (size_t) ctx->num_sms * 16), 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(),
+                  ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl, (const unsigned *) (tl + R));
+    } else
+        LAUNCH_ON(ctx, strm, k_bm_select, R, 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
+                  ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) nullptr, (const unsigned *) nullptr);
+    return 0;
+}
+
+// Disparity argmin / shape flags of the slots [s0, s1) from their summed-area planes, tied minima redone like std::sort
+int launch_stereo_argmin(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int s0, int s1, cudaStream_t strm)
+{
+    if (s1 <= s0) return 0;
+    const PassGeom pg = pass_geom(pc);
+    // every position could be tied (a flat light field): room for all of them
+    if (ctx->stielist.ensure(((size_t) P.nslots * P.st_stride + 1) * 8)) return 1;
+    uint2 *sl = ctx->stielist.as<uint2>();
+    unsigned *sc = reinterpret_cast<unsigned *>(sl + (size_t) P.nslots * P.st_stride);
+    CK(cudaMemsetAsync(sc, 0, 4, strm));
+    TieGeom tg{};
+    tg.plane_stride = P.st_stride; tg.w = (int) pc.wb; tg.nDisp = (int) pc.nDisp; tg.lo = P.st_lo; tg.nstrips = P.st_strips; tg.SR = P.st_SR;
+    tg.plane = (unsigned) pg.plane;
+    for (int s = 0; s < P.nslots; s++) tg.sai[s] = P.stereo_sai[s];
+    for (int s = s0; s < s1; s++) {
+        const int st = P.stereo_sai[s];
+        LAUNCH_ON(ctx, strm, k_stereo_argmin, grid_for(ctx, P.st_stride, 128), 128, 0, ctx->sums.as<float>() + (size_t) s * pg.nd2 * P.st_stride, P.st_stride,
+                  (int) pc.wb, (int) pc.nDisp, P.st_lo, P.st_row_end, P.st_col_end, P.st_strips, P.st_SR, pg.threshold,
+                  ctx->first.as<unsigned>() + (size_t) st * pg.plane, ctx->shape.as<unsigned char>() + (size_t) st * pg.plane, (unsigned) s, sl, sc);
+    }
+    const size_t smem_t = (size_t) 32 * LF_MAXNS2 * sizeof(LfPair);
+    CK(cudaFuncSetAttribute((const void *) k_stereo_ties, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_t));
+    LAUNCH_ON(ctx, strm, k_stereo_ties, ctx->num_sms * 4, 32, smem_t, tg, ctx->sums.as<float>(), (const uint2 *) sl, (const unsigned *) sc,
+              ctx->first.as<unsigned>());
+    return 0;
+}
+
+// Group kernel for the reference patches [r0, r1) (gather, transforms, shrinkage, inverses, staging for the aggregation)
+int launch_groups(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, bool partial, int r0, int r1)
+{
+    if (r1 <= r0) return 0;
+    const PassGeom pg = pass_geom(pc);
+    const size_t plane = pg.plane;
+    const int R = pg.R;
     GroupArgs ga{};
     ga.gmask = ctx->gmask.as<unsigned short>(); ga.shape_lut = ctx->shape_lut.as<GroupShape>();
     ga.act = partial ? ctx->act.as<unsigned char>() : nullptr; ga.partial = partial ? 1 : 0; ga.use_sd = (int) pc.useSD;
     ga.C = pc.C; ga.asw = pc.asw; ga.A = pc.A; ga.k = pc.k; ga.log2k = pc.k == 8 ? 3 : 4; ga.N = pc.N; ga.w = pc.wb; ga.h = pc.hb;
-    ga.pst = pst; ga.nc = nc;
+    ga.pst = pst; ga.nc = pg.nc; ga.r0 = r0;
     // row padding removes the shared-memory bank conflicts of the 2-D passes (3 CTAs/SM without it measured slower)
     ga.RS = pc.tau_2D == LFBM5D_ID ? pc.k : pc.k + 1;
     ga.PS = pc.k * ga.RS;
@@ -619,48 +656,135 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     ga.first = ctx->first.as<unsigned>(); ga.shape = ctx->shape.as<unsigned char>();
     ga.nsym = ctx->nsym.as<float>(); ga.bsym = ctx->bsym.as<float>();
     ga.numsym = ctx->numsym.as<float>(); ga.densym = ctx->densym.as<float>();
-    ga.zbuf = ctx->zbuf.as<float>(); ga.wbuf = ctx->wbuf.as<float>(); ga.ent = ctx->spos.as<unsigned>(); ga.R = (int) R;
+    ga.zbuf = ctx->zbuf.as<float>(); ga.wbuf = ctx->wbuf.as<float>(); ga.ent = ctx->spos.as<unsigned>(); ga.R = R;
     ga.win = win;
+    const int nblk = r1 - r0;
     const size_t smem = (size_t) pc.N * pc.A * ga.PS * 4 * (pc.step == 2 ? 2 : 1);
     void (*kfn)(GroupArgs) = pc.step == 1 ? (pc.asw == 3 ? k_groups<1, 3> : k_groups<1, 1>)
                                           : (pc.asw == 3 ? k_groups<2, 3> : k_groups<2, 1>);
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     if (pc.step == 1 && pc.tau_2D == LFBM5D_ID && pc.k == 16 && pc.asw == 3 && pc.N <= 8 && pc.tau_5D != LFBM5D_DCT && !pc.useSD) {
         // register-resident path (no 2-D transform to stage); patches that contribute zeros read the zero block behind nsym
-        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-        if (pc.C == 3) k_groups_id16<3><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
-        else k_groups_id16<1><<<R, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);       // validate(): C is 1 or 3
+        if (pc.C == 3) k_groups_id16<3><<<nblk, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);
+        else k_groups_id16<1><<<nblk, 256, 0, ctx->stream>>>(ga, 0x8000000080000000ull);       // validate(): C is 1 or 3
     }
     else if (pc.step == 2 && pc.tau_2D == LFBM5D_DCT && pc.k == 8 && pc.asw == 3 && pc.N <= 16 && pc.tau_5D == LFBM5D_HAAR && !pc.useSD) {
         // packed X/E path: FP32x2 forward transforms, two rows per lane in the inverses
-        CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
-        CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
         void (*k8)(GroupArgs, unsigned long long) = pc.C == 3 ? k_groups_w8<3> : k_groups_w8<1>;       // validate(): C is 1 or 3
         const size_t smem8 = (size_t) 16 * 9 * W8_PS * 8;
         CK(cudaFuncSetAttribute((const void *) k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem8));
-        k8<<<R, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
+        k8<<<nblk, W8_NT, smem8, ctx->stream>>>(ga, 0x8000000080000000ull);
     }
     else
-        kfn<<<R, 256, smem, ctx->stream>>>(ga);
+        kfn<<<nblk, 256, smem, ctx->stream>>>(ga);
     ctx->stats.kernel_launches++;
-    if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
-    {   // ordered aggregation of the staged patches
-        AggArgs aa{};
-        aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
-        while ((1u << aa.log2N) < pc.N) aa.log2N++;
-        aa.w = pc.wb; aa.h = pc.hb; aa.nc = nc;
-        aa.R = (int) R; aa.ent = ctx->spos.as<unsigned>();
-        aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
-        aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
-        aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
-        aa.win = win;
-        dim3 grid((pc.wb + 15) / 16, (pc.hb + 15) / 16, pc.A);
-        void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
-        if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
-        else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
-        else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
-        LAUNCH(ctx, kagg, grid, 256, 0, aa);
+    return 0;
+}
+
+// Ordered aggregation of the staged patches of the reference rows [a_lo, a_hi) into the pixel rows [y_lo, y_hi)
+int launch_aggregate(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int y_lo, int y_hi, int a_lo, int a_hi)
+{
+    if (y_hi <= y_lo || a_hi <= a_lo) return 0;
+    const PassGeom pg = pass_geom(pc);
+    AggArgs aa{};
+    aa.C = pc.C; aa.A = pc.A; aa.k = pc.k; aa.N = pc.N; aa.log2N = 0;
+    while ((1u << aa.log2N) < pc.N) aa.log2N++;
+    aa.w = pc.wb; aa.h = pc.hb; aa.nc = pg.nc;
+    aa.R = pg.R; aa.ent = ctx->spos.as<unsigned>();
+    aa.zbuf = ctx->zbuf.as<float>(); aa.wbuf = ctx->wbuf.as<float>();
+    aa.numsym = ctx->numsym.as<float>(); aa.densym = ctx->densym.as<float>();
+    aa.arange = ctx->arange.as<int>(); aa.brange = ctx->brange.as<int>();
+    aa.win = win;
+    aa.y_lo = y_lo; aa.y_hi = y_hi; aa.a_min = a_lo; aa.a_max = a_hi - 1;
+    aa.ty0 = y_lo / 16;
+    dim3 grid((pc.wb + 15) / 16, (y_hi + 15) / 16 - aa.ty0, pc.A);
+    void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
+    if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
+    else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
+    else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
+    LAUNCH(ctx, kagg, grid, 256, 0, aa);
+    return 0;
+}
+
+// partial-window branch: which reference patches of SAI pst still hold a pixel without weight
+int launch_active_refs(lfbm5d_ctx *ctx, const PassCfg &pc, int pst, unsigned **cnt_out)
+{
+    const size_t Rr = pc.rows.size() * pc.cols.size();
+    if (ctx->act.ensure(Rr + 16)) return 1;
+    unsigned *cnt = reinterpret_cast<unsigned *>(ctx->act.as<unsigned char>() + ((Rr + 3) & ~(size_t) 3));
+    CK(cudaMemsetAsync(cnt, 0, 12, ctx->stream));
+    LAUNCH(ctx, k_active_refs, (unsigned) ((Rr + 255) / 256), 256, 0,
+           ctx->densym.as<float>() + (size_t) pst * pc.C * pc.wb * pc.hb, ctx->rows.as<int>(), ctx->cols.as<int>(), (int) pc.cols.size(), (int) Rr,
+           (int) pc.wb, (int) pc.k, ctx->act.as<unsigned char>(), cnt);
+    *cnt_out = cnt;
+    return 0;
+}
+
+// the zero blocks behind nsym / bsym that the packed / register-resident group kernels gather "reads as zeros" patches from
+int clear_zero_blocks(lfbm5d_ctx *ctx, const PassCfg &pc)
+{
+    const size_t plane = (size_t) pc.wb * pc.hb;
+    CK(cudaMemsetAsync(ctx->nsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+    if (pc.step == 2) CK(cudaMemsetAsync(ctx->bsym.as<float>() + (size_t) pc.A * pc.C * plane, 0, (size_t) pc.C * plane * 4, ctx->stream));
+    return 0;
+}
+
+// One core call on the padded device buffers of the window (nsym/bsym/numsym/densym/est0 already filled).
+// cst = slot the window was centred on: pst != cst is the partial-window branch (core:531-821 / :1332-1658).
+int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, int cst = -1)
+{
+    const bool partial = cst >= 0 && cst != pst;
+    if (ensure_tables(ctx)) return 1;
+    int act_ymax = -1, act_xmax = -1;       // partial-window branch: last row / column of a reference patch that is still processed
+    if (partial) {
+        unsigned *cnt = nullptr;
+        if (launch_active_refs(ctx, pc, pst, &cnt)) return 1;
+        unsigned h3[3] = { 0, 0, 0 };
+        CK(cudaMemcpyAsync(h3, cnt, 12, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (h3[0] == 0) return 0;       // nothing left to denoise in this SAI (core:160-165)
+        act_ymax = (int) h3[1]; act_xmax = (int) h3[2];
     }
+    const PassGeom pg = pass_geom(pc);
+    const int R = pg.R;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    SatPlan *Pp = sat_plan(ctx, pc, win, pst, partial, act_ymax, act_xmax);
+    if (!Pp) return 1;
+    const SatPlan &P = *Pp;
+    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + P.planes.size() * (size_t) P.pstrips) * 4, ctx->stream));
+    cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
+    if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
+    // Self matching (summed-area planes, selection) stays on the main stream; disparity matching (planes, argmin, ties) runs
+    // beside it on a second stream: the issue-bound plane kernels overlap with the bandwidth-bound argmin and the latency-bound
+    // selection / tie kernels of the other branch. The two launches use disjoint plane indices of bnd / progress.
+    cudaStream_t sB = ctx->stream3;
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(sB, ctx->ev_fork, 0));
+    // the disparity planes are launched first: they finish first and their argmin then runs under the self planes
+    if (launch_sat_stereo(ctx, pc, P, 0, P.nslots, sB)) return 1;
+    if (pg.nself > 0) {
+        LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) pg.nself * R), 256, 0, ctx->s_mir.as<float>(), 2 * pg.threshold, (size_t) pg.nself * R);   // core:3317
+        if (launch_sat_self(ctx, pc, P, 0, P.nself_groups, ctx->stream)) return 1;
+    }
+    if (ctx->timing) { CK(cudaEventRecord(sat1, ctx->stream)); CK(cudaEventRecord(ctx->ev_satb, sB)); }
+    // ---- selection ----
+    if (pg.nself > 0) { if (launch_self_select(ctx, pc, ctx->stream)) return 1; }
+    else
+        LAUNCH(ctx, k_bm_identity, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, (int) pc.wb, R, (int) pc.N,
+               ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+    if (launch_stereo_argmin(ctx, pc, P, 0, P.nslots, sB)) return 1;
+    CK(cudaEventRecord(ctx->ev_join, sB));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure(R * 2)) return 1;
+    LAUNCH(ctx, k_group_masks, (R + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, 0, (int) R, (int) pc.wb, (unsigned) pg.plane,
+           (int) pc.A, (int) pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (ctx->bm_only) { CK(cudaGetLastError()); return 0; }
+
+    // ---- groups, then the ordered aggregation of the staged patches ----
+    if (clear_zero_blocks(ctx, pc) || launch_groups(ctx, pc, win, pst, partial, 0, R)) return 1;
+    if (ctx->timing) CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    if (launch_aggregate(ctx, pc, win, 0, (int) pc.hb, 0, pg.nr)) return 1;
     CK(cudaGetLastError());
     ctx->stats.window_passes++;
     if (ctx->timing) {
@@ -1082,6 +1206,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
                       &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act, &ctx->rt_noisy, &ctx->rt_basic };
     for (auto b : all) b->release();
+    for (auto &e : ctx->sat_cache) { e->d_planes.release(); e->d_groups.release(); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -1385,3 +1510,5 @@ int lfbm5d_debug_block_matching(lfbm5d_ctx *ctx, int step, const lfbm5d_params *
 }
 
 } // extern "C"
+
+#include "team.cuh"

@@ -1,0 +1,840 @@
+// One light field on G GPUs — parallelism INSIDE a window pass (north_star's row-band partition).
+//
+// Rank g of a team owns the reference rows rows[a0_g .. a1_g) of the pass grid and the pixel rows P_g = [y0_g, y1_g) of the padded
+// planes (y0_g = rows[a0_g] - n: the first row its groups can touch). Its groups write into C_g = [y0_g, c1_g), c1_g =
+// rows[a1_g - 1] + n + k, which reaches O_g = [y1_g, c1_g) rows into the next rank's band ("search radius plus patch size").
+// Per pass:
+//   1. every rank builds the padded working set on C_g and the running estimate (channel 0) on P_g; the est0 rows are exchanged,
+//      so that every rank holds the complete planes block matching reads;
+//   2. block matching is PLANE parallel (the float32 summed-area recurrences run from the top-left corner of a plane: a plane is
+//      not split): the 703 self planes and the 8 x 169 disparity planes are dealt out; disparity results (argmin / shape maps of a
+//      SAI) go to everybody, the self candidates as per-rank top-(N+1) lists to the owner of the reference row, who merges them;
+//   3. groups (transforms, shrinkage) for the own reference rows; aggregation, still in the reference's order: on O_g the sums of
+//      rank g come BEFORE those of rank g + 1 (lower reference rows first), so rank g adds its patches on [c1_{g-1}, c1_g) first
+//      and sends the rows O_g to rank g + 1, which continues the very same float sums with its own patches and returns the final
+//      rows (rank g keeps them as a replica: it needs them to start the next pass that touches these SAIs).
+// No float operation changes its operands or its order: num / den, and therefore every later match list, are BIT-IDENTICAL to
+// the single-GPU run (tests/test_team_gpu.py). Exchanges are NCCL send/recv groups on the compute stream, or device copies
+// between G contexts on ONE device (emulated team: how the band logic is tested on a single GPU).
+#pragma once
+#include "team_kernels.cuh"
+#include <dlfcn.h>
+
+namespace {
+
+struct Band {
+    int a0 = 0, a1 = 0;          // own reference rows
+    int r0 = 0, r1 = 0;          // = a0 * nc, a1 * nc
+    int y0 = 0, y1 = 0;          // owned pixel rows (padded coordinates)
+    int c1 = 0;                  // own groups touch [y0, c1)
+    int pc1 = 0;                 // c1 of the previous rank (y0 for rank 0): rows [y0, pc1) continue the previous rank's sums
+    int i0 = 0, i1 = 0;          // interior (unpadded) rows of [y0, y1)
+    int j0 = 0, j1 = 0;          // interior rows of [y0, c1): what the rank keeps up to date of num / den
+};
+
+enum TeamBuf { TB_EST0, TB_FIRST, TB_SHAPE, TB_PKEY_SEND, TB_PKEY_ALL, TB_PCNT_SEND, TB_PCNT_ALL, TB_NUMSYM, TB_DENSYM, TB_COUNTERS,
+               TB_S_AT, TB_S_MIR, TB_GSEND, TB_GRECV, TB_NBUF };
+
+struct TeamSeg { int src, dst; int sbuf, dbuf; size_t soff, doff, bytes; };      // dst < 0: to every other rank, same place
+
+// ---- NCCL through dlopen: the library has no link-time dependency on it (single-GPU users never load it) ----
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.h) return 0;
+    const char *names[] = { getenv("LFBM5D_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) {
+        if (!nm) continue;
+        g_nccl.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail("libnccl.so.2 not found (set LFBM5D_NCCL_LIB, or import torch first: it brings its own)");
+#define NCCL_SYM(field, name) *(void **) (&g_nccl.field) = dlsym(g_nccl.h, name); if (!g_nccl.field) return fail(std::string("NCCL symbol missing: ") + name)
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv"); NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    return 0;
+}
+#define NCK(x) do { int r_ = (x); if (r_ != 0) return fail(std::string(#x) + ": " + g_nccl.GetErrorString(r_)); } while (0)
+
+} // namespace
+
+struct lfbm5d_team {
+    int world = 1;
+    std::vector<lfbm5d_ctx *> local;       // contexts of the ranks living in this process (emulated: all of them; NCCL: one)
+    std::vector<int> local_rank;
+    bool owns_ctx = false;
+    void *comm = nullptr;                  // ncclComm_t (NCCL teams)
+    // step state shared by all ranks (every rank takes the same decisions from the same exchanged counts)
+    StepState ss;
+    std::vector<Band> bands;
+    std::vector<float *> d_noisy, d_basic; // per local rank
+    unsigned long long bytes_exchanged = 0;
+    unsigned passes_redone = 0;
+};
+
+namespace {
+
+struct TeamCtxBufs { DevBuf pkey_send, pkey_all, pcnt_send, pcnt_all, counters, gsend, grecv; };
+std::vector<std::pair<lfbm5d_ctx *, TeamCtxBufs *>> g_team_bufs;
+TeamCtxBufs *team_bufs(lfbm5d_ctx *ctx)
+{
+    for (auto &e : g_team_bufs) if (e.first == ctx) return e.second;
+    g_team_bufs.emplace_back(ctx, new TeamCtxBufs());
+    return g_team_bufs.back().second;
+}
+void team_bufs_release(lfbm5d_ctx *ctx)
+{
+    for (size_t i = 0; i < g_team_bufs.size(); i++)
+        if (g_team_bufs[i].first == ctx) {
+            TeamCtxBufs *b = g_team_bufs[i].second;
+            DevBuf *all[] = { &b->pkey_send, &b->pkey_all, &b->pcnt_send, &b->pcnt_all, &b->counters, &b->gsend, &b->grecv };
+            for (auto d : all) d->release();
+            delete b;
+            g_team_bufs.erase(g_team_bufs.begin() + i);
+            return;
+        }
+}
+
+char *team_ptr(lfbm5d_ctx *ctx, int id)
+{
+    TeamCtxBufs *b = team_bufs(ctx);
+    switch (id) {
+        case TB_EST0: return ctx->est0.as<char>();
+        case TB_FIRST: return ctx->first.as<char>();
+        case TB_SHAPE: return ctx->shape.as<char>();
+        case TB_PKEY_SEND: return b->pkey_send.as<char>();
+        case TB_PKEY_ALL: return b->pkey_all.as<char>();
+        case TB_PCNT_SEND: return b->pcnt_send.as<char>();
+        case TB_PCNT_ALL: return b->pcnt_all.as<char>();
+        case TB_NUMSYM: return ctx->numsym.as<char>();
+        case TB_DENSYM: return ctx->densym.as<char>();
+        case TB_COUNTERS: return b->counters.as<char>();
+        case TB_S_AT: return ctx->s_at.as<char>();
+        case TB_S_MIR: return ctx->s_mir.as<char>();
+        case TB_GSEND: return b->gsend.as<char>();
+        case TB_GRECV: return b->grecv.as<char>();
+        default: return nullptr;
+    }
+}
+
+// Execute a list of segments. NCCL team: one group of sends / receives on the compute stream of the (single) local rank.
+// Emulated team: device copies between the contexts, fenced by device-wide synchronisations (test path).
+int team_exchange(lfbm5d_team *T, const std::vector<TeamSeg> &segs)
+{
+    if (segs.empty()) return 0;
+    if (T->comm) {
+        lfbm5d_ctx *ctx = T->local[0];
+        const int me = T->local_rank[0];
+        bool any = false;
+        for (const TeamSeg &s : segs) if (s.bytes && (s.src == me || s.dst == me || s.dst < 0)) { any = true; break; }
+        if (!any) return 0;
+        NCK(g_nccl.GroupStart());
+        for (const TeamSeg &s : segs) {
+            if (!s.bytes) continue;
+            if (s.dst < 0) {
+                if (s.src == me) { for (int d = 0; d < T->world; d++) if (d != me) NCK(g_nccl.Send(team_ptr(ctx, s.sbuf) + s.soff, s.bytes, 0, d, T->comm, ctx->stream)); }
+                else NCK(g_nccl.Recv(team_ptr(ctx, s.dbuf) + s.doff, s.bytes, 0, s.src, T->comm, ctx->stream));
+                if (s.src == me) T->bytes_exchanged += s.bytes * (T->world - 1);
+            } else if (s.src == s.dst) {
+                if (s.src == me) CK(cudaMemcpyAsync(team_ptr(ctx, s.dbuf) + s.doff, team_ptr(ctx, s.sbuf) + s.soff, s.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            } else {
+                if (s.src == me) { NCK(g_nccl.Send(team_ptr(ctx, s.sbuf) + s.soff, s.bytes, 0, s.dst, T->comm, ctx->stream)); T->bytes_exchanged += s.bytes; }
+                if (s.dst == me) NCK(g_nccl.Recv(team_ptr(ctx, s.dbuf) + s.doff, s.bytes, 0, s.src, T->comm, ctx->stream));
+            }
+        }
+        NCK(g_nccl.GroupEnd());
+        return 0;
+    }
+    CK(cudaDeviceSynchronize());
+    cudaStream_t st = T->local[0]->stream;
+    for (const TeamSeg &s : segs) {
+        if (!s.bytes) continue;
+        for (int d = 0; d < T->world; d++) {
+            if (s.dst >= 0 ? d != s.dst : d == s.src) continue;
+            CK(cudaMemcpyAsync(team_ptr(T->local[d], s.dbuf) + s.doff, team_ptr(T->local[s.src], s.sbuf) + s.soff, s.bytes, cudaMemcpyDeviceToDevice, st));
+            if (d != s.src) T->bytes_exchanged += s.bytes;
+        }
+    }
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// Row bands of a pass grid for G ranks. Only as many ranks get rows as the no-triple-overlap rule allows (c1_g <= y0_{g+2}: a pixel
+// row sees the groups of at most two ranks); the others own nothing and only take part in the block matching.
+std::vector<Band> team_bands(const PassCfg &pc, int G)
+{
+    const int nr = (int) pc.rows.size(), nc = (int) pc.cols.size(), n = (int) pc.n, k = (int) pc.k, hb = (int) pc.hb, H = (int) pc.H;
+    int Ge = G;
+    std::vector<int> a0;
+    for (; Ge >= 1; Ge--) {
+        a0.assign(Ge + 1, 0);
+        for (int g = 0; g <= Ge; g++) a0[g] = (int) ((long long) nr * g / Ge);
+        bool ok = true;
+        for (int g = 0; g < Ge; g++) if (a0[g + 1] <= a0[g]) ok = false;
+        for (int g = 0; ok && g + 2 < Ge; g++)
+            if (pc.rows[a0[g + 1] - 1] + n + k > pc.rows[a0[g + 2]] - n) ok = false;
+        if (ok || Ge == 1) break;
+    }
+    std::vector<Band> B(G);
+    for (int g = 0; g < G; g++) {
+        Band &b = B[g];
+        if (g < Ge) {
+            b.a0 = a0[g]; b.a1 = a0[g + 1];
+            b.y0 = g == 0 ? 0 : pc.rows[b.a0] - n;
+            b.y1 = g == Ge - 1 ? hb : pc.rows[a0[g + 1]] - n;
+            b.c1 = g == Ge - 1 ? hb : std::min(hb, pc.rows[b.a1 - 1] + n + k);
+            b.pc1 = g == 0 ? 0 : B[g - 1].c1;
+        } else { b.a0 = b.a1 = nr; b.y0 = b.y1 = b.c1 = b.pc1 = hb; }
+        b.r0 = b.a0 * nc; b.r1 = b.a1 * nc;
+        b.i0 = std::min(std::max(b.y0 - n, 0), H); b.i1 = std::min(std::max(b.y1 - n, 0), H);
+        b.j0 = b.i0; b.j1 = std::min(std::max(b.c1 - n, 0), H);
+        if (g == 0) { b.i0 = 0; b.j0 = 0; }
+    }
+    return B;
+}
+
+// Deal the offset planes of a pass out: disparity slots evenly (whole SAIs: their argmin needs all 169 planes), then the self
+// groups in contiguous runs so that every rank ends up with about the same number of planes.
+struct PlaneShare { int s0, s1, sg0, sg1, pl0, pl1; };
+std::vector<PlaneShare> team_planes(const SatPlan &P, int G)
+{
+    std::vector<PlaneShare> S(G);
+    const int per_slot = P.groups_per_slot * P.groups_per_slot;      // planes of a disparity slot
+    const double total = (double) P.nself_planes + (double) P.nslots * per_slot;
+    int sg = 0;
+    double cum = 0.0;
+    for (int g = 0; g < G; g++) {
+        PlaneShare &s = S[g];
+        s.s0 = (int) ((long long) P.nslots * g / G); s.s1 = (int) ((long long) P.nslots * (g + 1) / G);
+        s.sg0 = sg;
+        cum += (double) (s.s1 - s.s0) * per_slot;
+        const double goal = total * (g + 1) / G;          // cumulative: rounding does not pile up on the last rank
+        if (g == G - 1) sg = P.nself_groups;
+        else
+            while (sg < P.nself_groups && cum + P.groups[sg].nplanes / 2.0 <= goal) { cum += P.groups[sg].nplanes; sg++; }
+        s.sg1 = sg;
+        s.pl0 = s.sg0 < P.nself_groups ? P.groups[s.sg0].first_plane : P.nself_planes;
+        s.pl1 = s.sg1 < P.nself_groups ? P.groups[s.sg1].first_plane : P.nself_planes;
+    }
+    return S;
+}
+
+int team_ensure(lfbm5d_team *T, lfbm5d_ctx *ctx, const PassCfg &pc)
+{
+    const PassGeom pg = pass_geom(pc);
+    TeamCtxBufs *b = team_bufs(ctx);
+    const size_t NM = pc.N + 1, G = (size_t) T->world;
+    if (pg.nself > 0 && (b->pkey_send.ensure((size_t) pg.R * NM * 8) || b->pkey_all.ensure(G * pg.R * NM * 8) || b->pcnt_send.ensure((size_t) pg.R * 4) ||
+                         b->pcnt_all.ensure(G * pg.R * 4))) return 1;
+    if (b->counters.ensure(G * 64 * 8 + 64)) return 1;
+    return 0;
+}
+
+// ---- one core call of the team (all ranks in lockstep; `pst == cst` or the partial-window branch) ----
+// Returns through *cov the number of covered entries of LF_denoised_percent (summed over the ranks).
+int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, int cst, unsigned long long *cov)
+{
+    const bool partial = cst >= 0 && cst != pst;
+    const int G = T->world, nl = (int) T->local.size();
+    const PassGeom pg = pass_geom(pc);
+    const size_t plane = pg.plane, NM = pc.N + 1;
+    const int C = (int) pc.C, wb = (int) pc.wb;
+    std::vector<SatPlan *> plans(nl);
+    std::vector<PlaneShare> share;
+    // ---- block matching: own planes ----
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const int g = T->local_rank[l];
+        CK(cudaSetDevice(ctx->device));
+        if (ensure_tables(ctx)) return 1;
+        if (partial) {      // active reference patches of the own rows; block matching keeps its full extents in the team path
+            unsigned *cnt = nullptr;
+            if (launch_active_refs(ctx, pc, pst, &cnt)) return 1;
+        }
+        SatPlan *Pp = sat_plan(ctx, pc, win, pst, false, -1, -1);
+        if (!Pp) return 1;
+        plans[l] = Pp;
+        const SatPlan &P = *Pp;
+        if (share.empty()) share = team_planes(P, G);
+        const PlaneShare &sh = share[g];
+        CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + P.planes.size() * (size_t) P.pstrips) * 4, ctx->stream));
+        cudaStream_t sB = ctx->stream3;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(sB, ctx->ev_fork, 0));
+        if (launch_sat_stereo(ctx, pc, P, sh.s0, sh.s1, sB)) return 1;
+        if (pg.nself > 0 && sh.pl1 > sh.pl0) {
+            LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) (sh.pl1 - sh.pl0) * pg.R), 256, 0, ctx->s_mir.as<float>() + (size_t) sh.pl0 * pg.R, 2 * pg.threshold,
+                   (size_t) (sh.pl1 - sh.pl0) * pg.R);   // core:3317
+            if (launch_sat_self(ctx, pc, P, sh.sg0, sh.sg1, ctx->stream)) return 1;
+        }
+        if (pg.nself > 0) {
+            SelGeom sg{};
+            sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
+            sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
+            TeamCtxBufs *b = team_bufs(ctx);
+            void (*kp)(SelGeom, const float *, const float *, int, int, unsigned *, unsigned long long *) = nullptr;
+            switch (pc.N) {
+                case 2: kp = k_bm_partial<3>; break;
+                case 4: kp = k_bm_partial<5>; break;
+                case 8: kp = k_bm_partial<9>; break;
+                case 16: kp = k_bm_partial<17>; break;
+                default: kp = k_bm_partial<33>; break;
+            }
+            LAUNCH(ctx, kp, (pg.R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), sh.pl0, sh.pl1, b->pcnt_send.as<unsigned>(),
+                   b->pkey_send.as<unsigned long long>());
+        }
+        if (launch_stereo_argmin(ctx, pc, P, sh.s0, sh.s1, sB)) return 1;
+        CK(cudaEventRecord(ctx->ev_join, sB));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    const SatPlan &P0 = *plans[0];
+    {   // ---- exchange: disparity maps to everybody, partial candidate lists to the owners of the reference rows ----
+        std::vector<TeamSeg> segs;
+        for (int g = 0; g < G; g++)
+            for (int s = share[g].s0; s < share[g].s1; s++) {
+                const int st = P0.stereo_sai[s];
+                segs.push_back({ g, -1, TB_FIRST, TB_FIRST, (size_t) st * plane * 4, (size_t) st * plane * 4, plane * 4 });
+                segs.push_back({ g, -1, TB_SHAPE, TB_SHAPE, (size_t) st * plane, (size_t) st * plane, plane });
+            }
+        if (pg.nself > 0)
+            for (int g = 0; g < G; g++)
+                for (int h = 0; h < G; h++) {
+                    const Band &bh = T->bands[h];
+                    const size_t nrp = (size_t) (bh.r1 - bh.r0);
+                    segs.push_back({ g, h, TB_PKEY_SEND, TB_PKEY_ALL, (size_t) bh.r0 * NM * 8, ((size_t) g * pg.R + bh.r0) * NM * 8, nrp * NM * 8 });
+                    segs.push_back({ g, h, TB_PCNT_SEND, TB_PCNT_ALL, (size_t) bh.r0 * 4, ((size_t) g * pg.R + bh.r0) * 4, nrp * 4 });
+                }
+        if (team_exchange(T, segs)) return 1;
+    }
+    bool redo = false;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // ---- merged selection, groups and the first part of the aggregation: rows [pc1, c1) ----
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            const int g = T->local_rank[l];
+            const Band &bd = T->bands[g];
+            TeamCtxBufs *b = team_bufs(ctx);
+            CK(cudaSetDevice(ctx->device));
+            unsigned long long *cnts = b->counters.as<unsigned long long>() + (size_t) g * 64;
+            CK(cudaMemsetAsync(cnts, 0, 64 * 8, ctx->stream));
+            const int nown = bd.r1 - bd.r0;
+            if (nown > 0) {
+                if (pg.nself > 0 && !redo) {
+                    SelGeom sg{};
+                    sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
+                    sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
+                    void (*km)(SelGeom, int, int, int, const unsigned *, const unsigned long long *, unsigned *, unsigned *, unsigned *) = nullptr;
+                    switch (pc.N) {
+                        case 2: km = k_bm_merge<3>; break;
+                        case 4: km = k_bm_merge<5>; break;
+                        case 8: km = k_bm_merge<9>; break;
+                        case 16: km = k_bm_merge<17>; break;
+                        default: km = k_bm_merge<33>; break;
+                    }
+                    LAUNCH(ctx, km, (nown + 127) / 128, 128, 0, sg, G, bd.r0, bd.r1, b->pcnt_all.as<unsigned>(), b->pkey_all.as<unsigned long long>(),
+                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), reinterpret_cast<unsigned *>(cnts + 1));
+                } else if (pg.nself > 0) {      // ties somewhere: every rank now holds the complete sums, the reference's selection as on one GPU
+                    if (launch_self_select(ctx, pc, ctx->stream)) return 1;
+                } else
+                    LAUNCH(ctx, k_bm_identity_rows, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, wb, bd.r0, bd.r1, (int) pc.N,
+                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+                if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure((size_t) pg.R * 2)) return 1;
+                LAUNCH(ctx, k_group_masks, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, bd.r0, bd.r1, wb, (unsigned) plane,
+                       (int) pc.A, pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
+                if (clear_zero_blocks(ctx, pc) || launch_groups(ctx, pc, win, pst, partial, bd.r0, bd.r1)) return 1;
+                if (launch_aggregate(ctx, pc, win, bd.pc1, bd.c1, bd.a0, bd.a1)) return 1;
+            }
+        }
+        {   // rows O_g = [y1, c1) go to the next rank, which continues the sums
+            std::vector<TeamSeg> segs;
+            for (int g = 0; g + 1 < G; g++) {
+                const Band &bd = T->bands[g];
+                if (bd.c1 <= bd.y1) continue;
+                for (int a = 0; a < (int) pc.A; a++) {
+                    if (!win.mask[a] || win.proc[a]) continue;
+                    for (int c = 0; c < C; c++) {
+                        const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y1 * wb) * 4, bytes = (size_t) (bd.c1 - bd.y1) * wb * 4;
+                        segs.push_back({ g, g + 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
+                        segs.push_back({ g, g + 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
+                    }
+                }
+            }
+            if (team_exchange(T, segs)) return 1;
+        }
+        // ---- second part of the aggregation: rows [y0, pc1) on top of the previous rank's sums; coverage and tie counts ----
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            const int g = T->local_rank[l];
+            const Band &bd = T->bands[g];
+            TeamCtxBufs *b = team_bufs(ctx);
+            CK(cudaSetDevice(ctx->device));
+            if (bd.r1 > bd.r0 && launch_aggregate(ctx, pc, win, bd.y0, bd.pc1, bd.a0, bd.a1)) return 1;
+            unsigned long long *cnts = b->counters.as<unsigned long long>() + (size_t) g * 64;
+            if (bd.i1 > bd.i0)
+                LAUNCH(ctx, k_count_cov_rows, grid_for(ctx, (size_t) pc.A * C * (bd.i1 - bd.i0) * pc.W), 256, 0, ctx->densym.as<float>(), win, (int) pc.W, (int) pc.H,
+                       C, (int) pc.n, (int) pc.k, bd.i0, bd.i1 - bd.i0, cnts);
+        }
+        {   // final rows [y0, pc1) back to the previous rank (its replica of O_{g-1}); counters to everybody
+            std::vector<TeamSeg> segs;
+            for (int g = 1; g < G; g++) {
+                const Band &bd = T->bands[g];
+                if (bd.pc1 <= bd.y0) continue;
+                for (int a = 0; a < (int) pc.A; a++) {
+                    if (!win.mask[a] || win.proc[a]) continue;
+                    for (int c = 0; c < C; c++) {
+                        const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y0 * wb) * 4, bytes = (size_t) (bd.pc1 - bd.y0) * wb * 4;
+                        segs.push_back({ g, g - 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
+                        segs.push_back({ g, g - 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
+                    }
+                }
+            }
+            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, 16 });
+            if (team_exchange(T, segs)) return 1;
+        }
+        // ---- every rank reads the same counters and takes the same decision ----
+        unsigned long long total_cov = 0, total_ties = 0;
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            CK(cudaSetDevice(ctx->device));
+            std::vector<unsigned long long> h((size_t) G * 64);
+            CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (l == 0) for (int g = 0; g < G; g++) { total_cov += h[(size_t) g * 64]; total_ties += h[(size_t) g * 64 + 1] & 0xffffffffull; }
+            ctx->stats.window_passes++;
+        }
+        *cov = total_cov;
+        if (total_ties == 0 || redo) break;
+        // Exact float ties among the selected distances of some reference patch: the reference's result then depends on its heap
+        // algorithm over the complete candidate sequence. Redo the pass from the padded accumulators with the complete sums on
+        // every rank (the planes are still there: only their exchange, the selection, the groups and the aggregation run again).
+        redo = true;
+        T->passes_redone++;
+        std::vector<TeamSeg> segs;
+        for (int g = 0; g < G; g++) {
+            const size_t off = (size_t) share[g].pl0 * pg.R * 4, bytes = (size_t) (share[g].pl1 - share[g].pl0) * pg.R * 4;
+            segs.push_back({ g, -1, TB_S_AT, TB_S_AT, off, off, bytes });
+            segs.push_back({ g, -1, TB_S_MIR, TB_S_MIR, off, off, bytes });
+        }
+        if (team_exchange(T, segs)) return 1;
+        for (int l = 0; l < nl; l++) {      // restore the accumulators of the window on the rows the pass wrote
+            lfbm5d_ctx *ctx = T->local[l];
+            const Band &bd = T->bands[T->local_rank[l]];
+            CK(cudaSetDevice(ctx->device));
+            if (bd.c1 > bd.y0)
+                LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) pc.A * (bd.c1 - bd.y0) * wb), 256, 0, T->d_noisy[l], pc.step == 2 ? T->d_basic[l] : (const float *) nullptr,
+                       ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
+                       ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.W, (int) pc.H, C, (int) pc.n, bd.y0, bd.c1 - bd.y0);
+        }
+        // est0 was overwritten on the own rows by k_pad_rows with the same values (num / den of the light field are unchanged)
+    }
+    return 0;
+}
+
+// running estimate of the window on the own rows + its exchange (every rank then holds the complete channel-0 planes)
+int team_est0_exchange(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win)
+{
+    const size_t plane = (size_t) pc.wb * pc.hb;
+    std::vector<TeamSeg> segs;
+    for (int g = 0; g < T->world; g++) {
+        const Band &bd = T->bands[g];
+        if (bd.y1 <= bd.y0) continue;
+        for (int a = 0; a < (int) pc.A; a++)
+            if (win.mask[a]) {
+                const size_t off = ((size_t) a * plane + (size_t) bd.y0 * pc.wb) * 4;
+                segs.push_back({ g, -1, TB_EST0, TB_EST0, off, off, (size_t) (bd.y1 - bd.y0) * pc.wb * 4 });
+            }
+    }
+    return team_exchange(T, segs);
+}
+
+// per-SAI counts of zero weights, summed over the ranks (window / SAI selection, bm5d.cpp:189-202, :318-333)
+int team_count_zero(lfbm5d_team *T, const std::vector<int> &items, bool padded, const PassCfg &pc, std::vector<unsigned long long> &out)
+{
+    const int G = T->world, nl = (int) T->local.size();
+    const int nit = (int) items.size();
+    if (nit > 60) return fail("too many SAIs in one count");
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const int g = T->local_rank[l];
+        const Band &bd = T->bands[g];
+        CK(cudaSetDevice(ctx->device));
+        unsigned long long *cnts = team_bufs(ctx)->counters.as<unsigned long long>() + (size_t) g * 64;
+        CK(cudaMemsetAsync(cnts, 0, 64 * 8, ctx->stream));
+        for (int i = 0; i < nit; i++) {
+            if (padded) {      // padded weights of window slot items[i], all channels, own rows [y0, y1)
+                if (bd.y1 > bd.y0)
+                    LAUNCH(ctx, k_count_zero_rows, grid_for(ctx, (size_t) pc.C * (bd.y1 - bd.y0) * pc.wb), 256, 0,
+                           ctx->densym.as<float>() + (size_t) items[i] * pc.C * pc.wb * pc.hb, (int) pc.C, (size_t) pc.wb * pc.hb, (int) pc.wb, bd.y0, bd.y1 - bd.y0, cnts + i);
+            } else if (bd.i1 > bd.i0)
+                LAUNCH(ctx, k_count_zero_rows, grid_for(ctx, (size_t) pc.C * (bd.i1 - bd.i0) * pc.W), 256, 0,
+                       ctx->den.as<float>() + (size_t) items[i] * pc.C * pc.W * pc.H, (int) pc.C, (size_t) pc.W * pc.H, (int) pc.W, bd.i0, bd.i1 - bd.i0, cnts + i);
+        }
+    }
+    std::vector<TeamSeg> segs;
+    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, (size_t) nit * 8 });
+    if (team_exchange(T, segs)) return 1;
+    out.assign(nit, 0);
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        CK(cudaSetDevice(ctx->device));
+        std::vector<unsigned long long> h((size_t) G * 64);
+        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (l == 0) for (int g = 0; g < G; g++) for (int i = 0; i < nit; i++) out[i] += h[(size_t) g * 64 + i];
+    }
+    return 0;
+}
+
+int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *const *d_noisy, float *const *d_basic, const unsigned *mask_)
+{
+    if (validate(p_, step)) return 1;
+    const int nl = (int) T->local.size();
+    StepState &S = T->ss;
+    S = StepState();
+    S.p = *p_; S.step = step;
+    const lfbm5d_params *p = &S.p;
+    const unsigned asize = S.asize();
+    S.mask.assign(mask_, mask_ + asize);
+    S.active = true;
+    S.tau_4D = p->tau_4D;
+    S.proc.assign(asize, 0);
+    S.remaining = 0;
+    for (unsigned st = 0; st < asize; st++) { S.proc[st] = !S.mask[st]; S.remaining += S.proc[st] == 0; }
+    S.max_proc = S.remaining;
+    S.docolor = p->chnls == 3 && p->color_space != LFBM5D_RGB;
+    S.pc = PassCfg();
+    if (make_passcfg(S.pc, step, p, S.tau_4D)) return 1;
+    S.tables_tau4 = S.tau_4D;
+    S.touched.assign(asize, 0);
+    S.passes = 0;
+    T->bands = team_bands(S.pc, T->world);
+    T->d_noisy.assign(d_noisy, d_noisy + nl);
+    T->d_basic.assign(nl, nullptr);
+    if (step == 2) T->d_basic.assign(d_basic, d_basic + nl);
+    const size_t each = S.each();
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const Band &bd = T->bands[T->local_rank[l]];
+        CK(cudaSetDevice(ctx->device));
+        ctx->sched.clear();
+        if (ctx->mask.ensure(asize * 4) || ctx->num.ensure(asize * each * 4) || ctx->den.ensure(asize * each * 4)) return 1;
+        CK(cudaMemcpyAsync(ctx->mask.p, S.mask.data(), asize * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (S.docolor && bd.j1 > bd.j0) {      // only the rows this rank's groups read (own band + the rows it shares with the next rank)
+            LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * p->width), 256, 0, T->d_noisy[l], ctx->mask.as<unsigned>(), asize,
+                   (int) p->width, (int) p->height, p->color_space, 1, bd.j0, bd.j1 - bd.j0);
+            if (step == 2)
+                LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * p->width), 256, 0, T->d_basic[l], ctx->mask.as<unsigned>(), asize,
+                       (int) p->width, (int) p->height, p->color_space, 1, bd.j0, bd.j1 - bd.j0);
+        }
+        CK(cudaMemsetAsync(ctx->num.p, 0, asize * each * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
+        if (setup_tables(ctx, step, p, S.tau_4D) || ensure_pass_buffers(ctx, S.pc) || upload_grid(ctx, S.pc) || team_ensure(T, ctx, S.pc)) return 1;
+    }
+    return 0;
+}
+
+// bm5d.cpp:182-202 for the team (the counts of zero weights are summed over the bands)
+int team_select(lfbm5d_team *T, unsigned &ps, unsigned &pt)
+{
+    StepState &S = T->ss;
+    const lfbm5d_params *p = &S.p;
+    const unsigned asize = S.asize(), cs = p->aheight / 2, ct = p->awidth / 2;
+    if (S.remaining == S.max_proc && S.mask[S.cst()]) { ps = cs; pt = ct; return 0; }
+    std::vector<int> need;
+    for (unsigned st = 0; st < asize; st++) if (!S.proc[st] && S.touched[st]) need.push_back((int) st);
+    std::vector<unsigned long long> zc(asize, (unsigned long long) S.each());
+    for (size_t b0 = 0; b0 < need.size(); b0 += 48) {
+        std::vector<int> chunk(need.begin() + b0, need.begin() + std::min(need.size(), b0 + 48));
+        std::vector<unsigned long long> h;
+        if (team_count_zero(T, chunk, false, S.pc, h)) return 1;
+        for (size_t i = 0; i < chunk.size(); i++) zc[chunk[i]] = h[i];
+    }
+    long long best = -1;
+    unsigned pst_g = 0;
+    for (unsigned st = 0; st < asize; st++) {
+        if (S.proc[st]) continue;
+        const long long z = (long long) (int) zc[st];     // the reference keeps the count in an int
+        if (z >= best) { pst_g = st; best = z; }
+    }
+    if (p->ang_major == LFBM5D_ROWMAJOR) { ps = pst_g / p->awidth; pt = pst_g - ps * p->awidth; }
+    else { pt = pst_g / p->aheight; ps = pst_g - pt * p->aheight; }
+    return 0;
+}
+
+// One angular window (bm5d.cpp:204-402), all ranks in lockstep
+int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
+{
+    StepState &S = T->ss;
+    const lfbm5d_params *p = &S.p;
+    const int step = S.step, nl = (int) T->local.size();
+    PassCfg &pc = S.pc;
+    const unsigned asize = S.asize(), asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
+    angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
+    angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
+    const unsigned cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
+    LfWindow win{};
+    win.A = (int) Aw;
+    unsigned n_unproc = 0;
+    for (unsigned s_a = 0; s_a < asw; s_a++)
+        for (unsigned t_a = 0; t_a < asw; t_a++) {
+            const unsigned s = s_a + min_s, t = t_a + min_t;
+            unsigned st, a;
+            if (p->ang_major == LFBM5D_ROWMAJOR) { st = s * p->awidth + t; a = s_a * asw + t_a; }
+            else { st = s + t * p->aheight; a = s_a + t_a * asw; }
+            win.st[a] = (int) st;
+            win.mask[a] = S.mask[st];
+            win.proc[a] = !S.mask[st];
+            n_unproc += S.mask[st] != 0;
+        }
+    if (n_unproc != Aw && S.tau_4D == LFBM5D_DCT) S.tau_4D = LFBM5D_SADCT;
+    if (S.tau_4D != S.tables_tau4) {
+        pc.tau_4D = S.tau_4D;
+        for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); if (setup_tables(T->local[l], step, p, S.tau_4D)) return 1; }
+        S.tables_tau4 = S.tau_4D;
+    }
+    for (int l = 0; l < nl; l++) {      // padded working set on the rows the own groups touch; running estimate on them as well
+        lfbm5d_ctx *ctx = T->local[l];
+        const Band &bd = T->bands[T->local_rank[l]];
+        CK(cudaSetDevice(ctx->device));
+        if (bd.c1 > bd.y0)
+            LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) Aw * (bd.c1 - bd.y0) * pc.wb), 256, 0, T->d_noisy[l], step == 2 ? T->d_basic[l] : (const float *) nullptr,
+                   ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
+                   ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, bd.y0, bd.c1 - bd.y0);
+    }
+    const unsigned max_unproc = n_unproc;
+    unsigned calls = 0;
+    while (n_unproc) {
+        unsigned pst_asw = 0;
+        if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
+        else {      // bm5d.cpp:318-333
+            std::vector<int> items;
+            for (unsigned a = 0; a < Aw; a++) if (win.proc[a] == 0) items.push_back((int) a);
+            std::vector<unsigned long long> hz;
+            if (team_count_zero(T, items, true, pc, hz)) return 1;
+            long long best = -1;
+            for (size_t i = 0; i < items.size(); i++) {
+                const long long z = (long long) (int) hz[i];
+                if (z >= best) { pst_asw = (unsigned) items[i]; best = z; }
+            }
+        }
+        if (calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937), own rows
+            for (int l = 0; l < nl; l++) {
+                lfbm5d_ctx *ctx = T->local[l];
+                const Band &bd = T->bands[T->local_rank[l]];
+                CK(cudaSetDevice(ctx->device));
+                if (bd.y1 > bd.y0)
+                    LAUNCH(ctx, k_est0_rows, grid_for(ctx, (size_t) Aw * (bd.y1 - bd.y0) * pc.wb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
+                           ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.wb, (int) pc.hb, (int) C, bd.y0, bd.y1 - bd.y0);
+            }
+        if (team_est0_exchange(T, pc, win)) return 1;
+        unsigned long long cnt = 0;
+        if (team_pass(T, pc, win, (int) pst_asw, (int) cst_asw, &cnt)) return 1;
+        calls++;
+        win.proc[pst_asw] += 1;
+        S.proc[win.st[pst_asw]] += 1;
+        for (int l = 0; l < nl; l++) {      // crop the accumulators back: the own band and the replica rows shared with the next rank
+            lfbm5d_ctx *ctx = T->local[l];
+            const Band &bd = T->bands[T->local_rank[l]];
+            CK(cudaSetDevice(ctx->device));
+            if (bd.j1 > bd.j0)
+                LAUNCH(ctx, k_unpad_rows, grid_for(ctx, (size_t) Aw * C * (bd.j1 - bd.j0) * W), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(),
+                       ctx->numsym.as<float>(), ctx->densym.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, bd.j0, bd.j1 - bd.j0);
+        }
+        // LF_denoised_percent (utilities_LF.cpp:967-995): float counter (saturates at 2^24), normalised without C
+        const float fcnt = (float) std::min<unsigned long long>(cnt, 16777216ull);
+        unsigned nmask = 0;
+        for (unsigned a = 0; a < Aw; a++) nmask += win.mask[a] == 1;
+        const float pct = fcnt * 100.0f / (float) nmask / (float) (H - pc.k + 1) / (float) (W - pc.k + 1);
+        if (pct >= 100.0f)
+            for (unsigned a = 0; a < Aw; a++)
+                if (win.proc[a] == 0) { win.proc[a] += 1; S.proc[win.st[a]] += 1; }
+        n_unproc = 0;
+        for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
+    }
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
+        ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
+    }
+    for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) S.touched[win.st[a]] = 1;
+    S.remaining = 0;
+    for (unsigned st = 0; st < asize; st++) S.remaining += S.proc[st] == 0;
+    S.passes++;
+    return 0;
+}
+
+// Final estimate on the rows each rank holds; gather != 0: the bands of `out` are then exchanged so that every rank has all of it
+int team_step_end(lfbm5d_team *T, float *const *d_out, int gather)
+{
+    StepState &S = T->ss;
+    const lfbm5d_params *p = &S.p;
+    const int nl = (int) T->local.size(), G = T->world;
+    const unsigned asize = S.asize(), C = p->chnls;
+    const int W = (int) p->width, H = (int) p->height;
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const Band &bd = T->bands[T->local_rank[l]];
+        CK(cudaSetDevice(ctx->device));
+        if (bd.j1 > bd.j0)
+            LAUNCH(ctx, k_final_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * W), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), T->d_noisy[l],
+                   T->d_basic[l], d_out[l], ctx->mask.as<unsigned>(), asize, W, H, (int) C, S.step, p->color_space, S.docolor ? 1 : 0, bd.j0, bd.j1 - bd.j0);
+        if (S.docolor) {      // rows this rank never transformed: leave them as the reference leaves its inputs (colour round trip)
+            const int lo[2] = { 0, bd.j1 }, hi[2] = { bd.j0, H };
+            for (int q = 0; q < 2; q++)
+                if (hi[q] > lo[q]) {
+                    LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (hi[q] - lo[q]) * W), 256, 0, T->d_noisy[l], ctx->mask.as<unsigned>(), asize, W, H,
+                           p->color_space, 2, lo[q], hi[q] - lo[q]);
+                    if (S.step == 2)
+                        LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (hi[q] - lo[q]) * W), 256, 0, T->d_basic[l], ctx->mask.as<unsigned>(), asize, W, H,
+                               p->color_space, 2, lo[q], hi[q] - lo[q]);
+                }
+        }
+        CK(cudaGetLastError());
+    }
+    if (gather && G > 1) {
+        const size_t nplanes = (size_t) asize * C;
+        size_t maxrows = 0;
+        for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (T->bands[g].i1 - T->bands[g].i0));
+        const size_t blk = nplanes * maxrows * W * 4;
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            const Band &bd = T->bands[T->local_rank[l]];
+            TeamCtxBufs *b = team_bufs(ctx);
+            CK(cudaSetDevice(ctx->device));
+            if (b->gsend.ensure(blk) || b->grecv.ensure(blk * G)) return 1;
+            if (bd.i1 > bd.i0)
+                LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_out[l], b->gsend.as<float>(), nplanes, W, H, bd.i0, bd.i1 - bd.i0, 0);
+        }
+        std::vector<TeamSeg> segs;
+        for (int g = 0; g < G; g++) {
+            const Band &bd = T->bands[g];
+            for (int h = 0; h < G; h++)
+                if (h != g) segs.push_back({ g, h, TB_GSEND, TB_GRECV, 0, (size_t) g * blk, nplanes * (size_t) (bd.i1 - bd.i0) * W * 4 });
+        }
+        if (team_exchange(T, segs)) return 1;
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            TeamCtxBufs *b = team_bufs(ctx);
+            CK(cudaSetDevice(ctx->device));
+            for (int g = 0; g < G; g++) {
+                const Band &bd = T->bands[g];
+                if (g == T->local_rank[l] || bd.i1 <= bd.i0) continue;
+                LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_out[l], b->grecv.as<float>() + (size_t) g * (blk / 4), nplanes, W, H,
+                       bd.i0, bd.i1 - bd.i0, 1);
+            }
+        }
+    }
+    for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); CK(cudaStreamSynchronize(T->local[l]->stream)); }
+    S.active = false;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int lfbm5d_team_create_emulated(lfbm5d_team **out, int device, int world)
+{
+    if (!out || world < 1 || world > 64) return fail("bad team arguments");
+    lfbm5d_team *T = new lfbm5d_team();
+    T->world = world; T->owns_ctx = true;
+    for (int g = 0; g < world; g++) {
+        lfbm5d_ctx *c = nullptr;
+        if (lfbm5d_create(&c, device)) { for (auto q : T->local) lfbm5d_destroy(q); delete T; return 1; }
+        T->local.push_back(c); T->local_rank.push_back(g);
+    }
+    *out = T;
+    return 0;
+}
+
+int lfbm5d_team_unique_id(char *id128)
+{
+    if (!id128) return fail("null argument");
+    if (nccl_load()) return 1;
+    NcclId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+
+int lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int world, const char *id128)
+{
+    if (!out || !ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail("bad team arguments");
+    if (nccl_load()) return 1;
+    CK(cudaSetDevice(ctx->device));
+    lfbm5d_team *T = new lfbm5d_team();
+    T->world = world;
+    T->local.push_back(ctx); T->local_rank.push_back(rank);
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = g_nccl.CommInitRank(&T->comm, world, id, rank);
+    if (rc != 0) { delete T; return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); }
+    *out = T;
+    return 0;
+}
+
+void lfbm5d_team_destroy(lfbm5d_team *T)
+{
+    if (!T) return;
+    for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); team_bufs_release(c); }
+    if (T->comm) g_nccl.CommDestroy(T->comm);
+    if (T->owns_ctx) for (auto c : T->local) lfbm5d_destroy(c);
+    delete T;
+}
+
+int lfbm5d_team_local_ranks(lfbm5d_team *T) { return T ? (int) T->local.size() : 0; }
+
+/* one LFBM5D step of ONE light field on the whole team; d_* are arrays of lfbm5d_team_local_ranks() device pointers (one copy of the
+ * light field per local rank, [asize][chnls][height][width] floats) */
+int lfbm5d_team_step(lfbm5d_team *T, int step, const lfbm5d_params *p, float *const *d_noisy_io, float *const *d_basic_io, const unsigned *sai_mask,
+                     float *const *d_out, int gather)
+{
+    if (!T || !p || !d_noisy_io || !sai_mask || !d_out || (step == 2 && !d_basic_io)) return fail("null argument");
+    if (step != 1 && step != 2) return fail("step must be 1 or 2");
+    if (team_step_begin(T, step, p, d_noisy_io, d_basic_io, sai_mask)) return 1;
+    const unsigned max_passes = T->local[0]->max_passes;
+    while (T->ss.remaining) {
+        unsigned ps = 0, pt = 0;
+        if (team_select(T, ps, pt) || team_window(T, ps, pt)) return 1;
+        if (max_passes && T->ss.passes >= max_passes) break;
+    }
+    return team_step_end(T, d_out, gather);
+}
+
+/* interior rows [*row_lo, *row_hi) of every SAI that rank `rank` owns in the step that ran last (its band of the output), and the
+ * rows [*row_lo, *keep_hi) it holds valid results for (its band + the rows shared with the next rank) */
+int lfbm5d_team_band(lfbm5d_team *T, int rank, int *row_lo, int *row_hi, int *keep_hi)
+{
+    if (!T || rank < 0 || rank >= (int) T->bands.size()) return fail("no band: run a step first");
+    const Band &b = T->bands[rank];
+    if (row_lo) *row_lo = b.i0;
+    if (row_hi) *row_hi = b.i1;
+    if (keep_hi) *keep_hi = b.j1;
+    return 0;
+}
+
+void lfbm5d_team_stats(lfbm5d_team *T, unsigned long long *bytes_exchanged, unsigned *passes_redone)
+{
+    if (!T) return;
+    if (bytes_exchanged) *bytes_exchanged = T->bytes_exchanged;
+    if (passes_redone) *passes_redone = T->passes_redone;
+}
+
+} // extern "C"

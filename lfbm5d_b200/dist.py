@@ -138,3 +138,16 @@ def run_step_windows(eng, step, prm, d_noisy, d_basic, mask, d_out, dist, device
             torch.cuda.synchronize(device)
     eng.step_end(d_out)
     return plan
+
+
+# ---- one light field on several GPUs: parallelism inside a window (csrc/team.cuh) -------------------------------------------
+def make_team(eng, dist, device):
+    """NCCL team over the ranks of the default process group: rank 0 draws the NCCL unique id, torch.distributed ships it."""
+    import torch
+    from . import Team
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(Team.unique_id()), dtype=torch.uint8).to(device)
+    dist.broadcast(uid, src=0)
+    return Team.nccl(eng, rank, world, bytes(uid.cpu().numpy().tobytes()))

@@ -1,0 +1,89 @@
+"""One light field on a team of ranks that split every window pass (csrc/team.cuh), emulated on ONE GPU: `world` contexts on the
+same device, exchanges as device copies. The band logic — plane-parallel block matching with merged candidate lists, row-band
+groups, the chained border sums of the ordered aggregation — must reproduce the single-context result BIT FOR BIT: basic,
+denoised, the colour-round-tripped inputs and the window schedule. (tests/dist_team_gpu.py runs the same check over NCCL.)"""
+import numpy as np
+import pytest
+
+import lfdata
+
+pytestmark = pytest.mark.gpu
+
+
+def run_single(L, eng, torch, noisy, mask, p1, p2):
+    w, b, o = noisy.clone(), torch.zeros_like(noisy), torch.zeros_like(noisy)
+    eng.step1_device(p1, w.data_ptr(), mask, b.data_ptr())
+    s1 = eng.schedule().copy()
+    eng.step2_device(p2, w.data_ptr(), b.data_ptr(), mask, o.data_ptr())
+    torch.cuda.synchronize()
+    return w, b, o, s1
+
+
+def run_team(L, torch, world, noisy, mask, p1, p2, gather):
+    team = L.Team.emulated(0, world)
+    ws = [noisy.clone() for _ in range(world)]
+    bs = [torch.zeros_like(noisy) for _ in range(world)]
+    outs = [torch.zeros_like(noisy) for _ in range(world)]
+    team.step(1, p1, [t.data_ptr() for t in ws], None, mask, [t.data_ptr() for t in bs], gather=gather)
+    bands1 = [team.band(g) for g in range(world)]
+    team.step(2, p2, [t.data_ptr() for t in ws], [t.data_ptr() for t in bs], mask, [t.data_ptr() for t in outs], gather=gather)
+    bands2 = [team.band(g) for g in range(world)]
+    torch.cuda.synchronize()
+    st = team.stats()
+    team.close()
+    return ws, bs, outs, bands1, bands2, st
+
+
+@pytest.mark.parametrize("world,aw,ah,H,W,C,masked", [(2, 3, 3, 200, 72, 3, False), (3, 4, 3, 330, 64, 3, True), (4, 3, 3, 340, 56, 3, False),
+                                                       (8, 3, 3, 620, 48, 3, False), (2, 3, 3, 150, 60, 1, False)])
+def test_team_bit_identical_to_single(world, aw, ah, H, W, C, masked, oracle):
+    import torch
+    import lfbm5d_b200 as L
+    dev = torch.device("cuda", 0)
+    clean = lfdata.synth_lf(aw, ah, H, W)[:, :C]
+    noisy = torch.from_numpy(oracle.add_noise(np.ascontiguousarray(clean), 15.0)).to(dev)
+    mask = np.ones(aw * ah, np.uint32)
+    if masked:
+        mask[5] = 0
+    p1 = L.make_params(15.0, 2.7, aw, ah, 1, W, H, C, 8, 18, 6, 16, 4, L.ID, L.DCT if masked else L.SADCT, L.HAAR)
+    p2 = L.make_params(15.0, 0.0, aw, ah, 1, W, H, C, 16, 18, 6, 8, 4, L.DCT, L.DCT if masked else L.SADCT, L.HAAR)
+    eng = L.LFBM5D(0)
+    w0, b0, o0, s0 = run_single(L, eng, torch, noisy, mask, p1, p2)
+    eng.close()
+    # complete results on every rank (gather) ...
+    ws, bs, outs, bands1, bands2, st = run_team(L, torch, world, noisy, mask, p1, p2, gather=1)
+    assert st["bytes_exchanged"] > 0
+    assert bands2[0][0] == 0 and bands2[-1][1] == H and all(bands2[g][1] == bands2[g + 1][0] for g in range(world - 1))
+    for g in range(world):
+        assert torch.equal(outs[g], o0), "denoised differs on rank %d" % g
+        assert torch.equal(ws[g], w0), "noisy round trip differs on rank %d" % g
+    # ... and band-resident results (no gather): every rank holds its band and the rows it shares with the next rank
+    ws, bs, outs, bands1, bands2, st = run_team(L, torch, world, noisy, mask, p1, p2, gather=0)
+    for g in range(world):
+        lo, hi, keep = bands1[g]
+        assert torch.equal(bs[g][:, :, lo:keep], b0[:, :, lo:keep]), "basic differs on rank %d" % g
+        lo, hi, keep = bands2[g]
+        assert torch.equal(outs[g][:, :, lo:keep], o0[:, :, lo:keep]), "denoised differs on rank %d" % g
+
+
+def test_team_ties_redo_the_selection(oracle):
+    """Quantised, partly flat light field: exact distance ties among the selected self matches make the team redo the pass's
+    selection from the complete sums (the re-implemented libstdc++ partial_sort), still bit-identical to one GPU."""
+    import torch
+    import lfbm5d_b200 as L
+    dev = torch.device("cuda", 0)
+    aw = ah = 3
+    H, W = 200, 64
+    clean = np.round(lfdata.synth_lf(aw, ah, H, W) / 64.0) * 64.0
+    clean[:, :, 60:140, 10:50] = 64.0
+    noisy = torch.from_numpy(clean.astype(np.float32)).to(dev)
+    mask = np.ones(9, np.uint32)
+    p1 = L.make_params(15.0, 2.7, aw, ah, 1, W, H, 3, 8, 18, 6, 16, 4, L.ID, L.SADCT, L.HAAR)
+    p2 = L.make_params(15.0, 0.0, aw, ah, 1, W, H, 3, 16, 18, 6, 8, 4, L.DCT, L.SADCT, L.HAAR)
+    eng = L.LFBM5D(0)
+    w0, b0, o0, s0 = run_single(L, eng, torch, noisy, mask, p1, p2)
+    eng.close()
+    ws, bs, outs, bands1, bands2, st = run_team(L, torch, 2, noisy, mask, p1, p2, gather=1)
+    assert st["passes_redone"] > 0
+    for g in range(2):
+        assert torch.equal(outs[g], o0) and torch.equal(ws[g], w0)
