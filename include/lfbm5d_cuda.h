@@ -132,7 +132,22 @@ int  lfbm5d_team_local_ranks(lfbm5d_team *team);      /* emulated: world; NCCL: 
 int  lfbm5d_team_step(lfbm5d_team *team, int step, const lfbm5d_params *p, float *const *d_noisy_io, float *const *d_basic_io,
                       const unsigned *sai_mask, float *const *d_out, int gather);
 int  lfbm5d_team_band(lfbm5d_team *team, int rank, int *row_lo, int *row_hi, int *keep_hi);
-void lfbm5d_team_stats(lfbm5d_team *team, unsigned long long *bytes_exchanged, unsigned *passes_redone);
+/* the same bands from the parameters alone (before a step runs): what a host driver uploads to rank `rank` is [row_lo, keep_hi) */
+int  lfbm5d_team_plan_band(int world, int rank, int step, const lfbm5d_params *p, int *row_lo, int *row_hi, int *keep_hi);
+/* rows [row_lo, row_hi) of every plane of every non-masked SAI between host arrays (asize pointers, as for lfbm5d_step1) and a device
+ * light field, asynchronously on the context's stream (lfbm5d_sync waits): the band-wise upload / download of a team's ranks */
+int  lfbm5d_copy_rows(lfbm5d_ctx *ctx, float *const *host, float *d_lf, const unsigned *sai_mask, unsigned asize, unsigned chnls,
+                      unsigned width, unsigned height, unsigned row_lo, unsigned row_hi, int to_device);
+int  lfbm5d_sync(lfbm5d_ctx *ctx);
+/* bytes this process sent so far; passes whose selection was redone from exchanged sums (fallback without peer view); reference
+ * patches whose exact distance ties were resolved through the peer view; whether the peer view (cudaIpc / NVLink loads) is in use */
+void lfbm5d_team_stats(lfbm5d_team *team, unsigned long long *bytes_exchanged, unsigned *passes_redone, unsigned long long *tie_patches,
+                       int *peer_view);
+/* per-phase device time (CUDA events on the first local rank): returns in out12 the ms accumulated since timing was switched on for
+ * pad, est0 exchange, block matching, match exchange, selection + groups + aggregation 1, border exchange, aggregation 2, border + counter
+ * exchange, and inside block matching: self planes, partial selection, disparity planes, disparity argmin */
+void lfbm5d_team_timing(lfbm5d_team *team, int on, float *out12);
+void lfbm5d_team_disable_peer_view(lfbm5d_team *team);   /* tests: force the exchange-and-redo fallback */
 
 /* ---- parity/debug exports (used by tests only) ---------------------------------------------------
  * One window pass (the reference's bm5d_1st_step / bm5d_2nd_step, `pst == cst` branch) on HOST padded

@@ -47,7 +47,7 @@ EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset
            "lfbm5d_debug_schedule", "lfbm5d_step_begin", "lfbm5d_step_window", "lfbm5d_step_end", "lfbm5d_step_accumulators",
            "lfbm5d_step_plan", "lfbm5d_step_force_sadct", "lfbm5d_step_window_ex", "lfbm5d_debug_block_matching", "lfbm5d_team_create_emulated", "lfbm5d_team_unique_id",
            "lfbm5d_team_create_nccl", "lfbm5d_team_destroy", "lfbm5d_team_local_ranks", "lfbm5d_team_step", "lfbm5d_team_band",
-           "lfbm5d_team_stats"]
+           "lfbm5d_team_stats", "lfbm5d_team_disable_peer_view", "lfbm5d_team_timing", "lfbm5d_team_plan_band", "lfbm5d_copy_rows", "lfbm5d_sync"]
 
 HOST_LIB_PATH = os.path.join(_HERE, "_lib", "liblfbm5d_host.so")
 HOST_EXPORTS = ["lfio_add_noise", "lfio_psnr"]           # include/lfbm5d_host_c.h
@@ -236,6 +236,18 @@ class LFBM5D(object):
                                         C.c_void_p(d_out)) != 0:
             raise RuntimeError("lfbm5d_step2_device: " + self.error())
 
+    def copy_rows(self, host_ptrs, d_lf, mask, asize, chnls, width, height, row_lo, row_hi, to_device):
+        """Rows [row_lo, row_hi) of every plane between host arrays (ctypes array of asize float pointers) and a device light field;
+        asynchronous on the engine's stream (sync() waits)."""
+        m = np.ascontiguousarray(mask, np.uint32)
+        if self.lib.lfbm5d_copy_rows(self.ctx, host_ptrs, C.c_void_p(d_lf), _up(m), int(asize), int(chnls), int(width), int(height),
+                                     int(row_lo), int(row_hi), int(to_device)) != 0:
+            raise RuntimeError("lfbm5d_copy_rows: " + self.error())
+
+    def sync(self):
+        if self.lib.lfbm5d_sync(self.ctx) != 0:
+            raise RuntimeError("lfbm5d_sync: " + self.error())
+
     # -- window-level entry points (see lfbm5d_b200/dist.py) -------------------------------------------
     def step_begin(self, step, prm, d_noisy, d_basic, mask):
         m = np.ascontiguousarray(mask, np.uint32)
@@ -293,6 +305,15 @@ class LFBM5D(object):
         if rc != 0:
             raise RuntimeError("lfbm5d_debug_pass: " + self.error())
         return (num, den, dbg) if debug else (num, den)
+
+
+def plan_band(world, rank, step, prm):
+    """(row_lo, row_hi, keep_hi) of rank `rank` in a team of `world` ranks for a step with parameters prm (before it runs)."""
+    lib = load_library()
+    lo, hi, keep = C.c_int(), C.c_int(), C.c_int()
+    if lib.lfbm5d_team_plan_band(int(world), int(rank), int(step), C.byref(prm), C.byref(lo), C.byref(hi), C.byref(keep)) != 0:
+        raise RuntimeError("lfbm5d_team_plan_band: " + lib.lfbm5d_last_error().decode())
+    return lo.value, hi.value, keep.value
 
 
 class Team(object):
@@ -360,6 +381,17 @@ class Team(object):
         return lo.value, hi.value, keep.value
 
     def stats(self):
-        b, r = C.c_ulonglong(), C.c_uint()
-        self.lib.lfbm5d_team_stats(self.handle, C.byref(b), C.byref(r))
-        return {"bytes_exchanged": int(b.value), "passes_redone": int(r.value)}
+        b, r, t, pv = C.c_ulonglong(), C.c_uint(), C.c_ulonglong(), C.c_int()
+        self.lib.lfbm5d_team_stats(self.handle, C.byref(b), C.byref(r), C.byref(t), C.byref(pv))
+        return {"bytes_exchanged": int(b.value), "passes_redone": int(r.value), "tie_patches": int(t.value), "peer_view": bool(pv.value)}
+
+    def timing(self, on=True):
+        """Switch the per-phase timing on / off; returns the ms accumulated so far for (pad, est0 exchange, block matching, match
+        exchange, selection + groups + aggregation 1, border exchange, aggregation 2, border + counter exchange; inside block matching:
+        self planes, partial selection, disparity planes, disparity argmin)."""
+        out = (C.c_float * 12)()
+        self.lib.lfbm5d_team_timing(self.handle, int(on), out)
+        return [float(x) for x in out]
+
+    def disable_peer_view(self):
+        self.lib.lfbm5d_team_disable_peer_view(self.handle)

@@ -25,6 +25,9 @@ struct SatGeom {
     const int *colmap;      // [w]
     int gp, nreg, rlast, nr;     // reference rows (self): lo + a*gp for a < nreg, plus rlast (index nr-1)
     unsigned long long negzero2; // packed (-0.f, -0.f) supplied at run time (see lf_mul2)
+    unsigned epoch;         // launch counter: tags the boundary words of this launch (stale words of earlier launches never match)
+    const float *frow;      // [plane][w] first row of every plane's sums, [plane][h] first column (k_sat_edges)
+    const float *fcol;
 };
 // One offset plane: d(y,x) = (img2[y+oy][x+ox] - img1[y][x])^2, oy shared by the group.
 struct SatPlane {
@@ -36,6 +39,7 @@ struct SatPlane {
 };
 // Up to 2*SAT_NW planes that share the two source images and the row offset: one CTA per (group, strip).
 #define SAT_NW 7          // warps per CTA; each warp sweeps two planes
+#define SAT_SUB 8         // steps per hand-off between neighbouring strips
 struct SatGroup {
     const float *img1, *img2;
     int oy, oxmin, nplanes, first_plane;
@@ -53,13 +57,13 @@ template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 // wavefront, one 64-bit shuffle per step); the img1 operand is shared, the img2 operands are adjacent ring entries, and all
 // floating-point work of a step runs as packed FP32x2 instructions (bit-identical per half).
 // The strips of a plane are pipelined across CTAs: strip c consumes the last column of strip c - 1 through global memory with
-// a per-(plane, strip) progress flag, and CTAs take their work from a ticket counter in strip-major order so that a producer
+// tagged 64-bit words (see the hand-off comment in the kernel), and CTAs take their work from a ticket counter in strip-major order so that a producer
 // has always started before its consumer (no deadlock). Source rows of both images are staged once per CTA with cp.async
 // into two 128(+K)-row shared-memory rings (row stride 64 floats: the skewed reads are bank-conflict free) and reused by all
 // planes of the group; squared differences are formed on the fly.
 template <bool SELF, int K>
 __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
-                                                          int ngroups, float *bnd, int *progress, int *ticket_counter)
+                                                          int ngroups, unsigned long long *bnd, int *ticket_counter)
 {
     extern __shared__ float s_dyn[];
     // source-row rings of img1 / img2: 128 rows + K mirror rows (slot s < K is also stored at s + 128, so that the
@@ -88,11 +92,11 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     const int oxo = PA.ox - G.oxmin;                   // column shift of plane A inside the img2 ring (plane B: +1)
     const int ymax = min(g.row_end - 1 + k - 1, h - 1);
     const size_t pstride = (size_t) g.pstrips * h;
-    float *bnd_prev = bnd + (size_t) pid * pstride + (size_t) (strip > 0 ? strip - 1 : 0) * h;
-    float *bnd_next = bnd + (size_t) pid * pstride + (size_t) strip * h;
+    // hand-off words of the last column of a strip: [plane][strip][row] = (sum, epoch << 16 | row)
+    const unsigned long long *bnd_prev = bnd + (size_t) pid * pstride + (size_t) (strip > 0 ? strip - 1 : 0) * h;
+    unsigned long long *bnd_next = bnd + (size_t) pid * pstride + (size_t) strip * h;
     const size_t bB = hasB ? pstride : 0;              // offset from plane A's boundary column to plane B's
-    const int *prog_prev = progress + (size_t) pid * g.pstrips + (strip > 0 ? strip - 1 : 0);
-    int *prog_next = progress + (size_t) pid * g.pstrips + strip;
+    const unsigned tag_hi = g.epoch << 16;
 
     auto load_rows = [&](int y0, int y1) {
         if (y1 > ymax) y1 = ymax;
@@ -115,15 +119,6 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
                 } else { *dst = 0.f; if (sl < K) dst[128 * 64] = 0.f; }
             }
         }
-    };
-    // squared difference of plane `pl` (0 = A, 1 = B) at source row y, ring column slot cs — cold paths only
-    auto dval = [&](int pl, int y, int cs) -> float {
-        const float a = R1[(y & 127) * 64 + cs];
-        const float b = R2[((y + G.oy) & 127) * 64 + cs + oxo + pl];
-        const float df = b - a;
-        float v = df * df;
-        if (SELF) { if (y >= g.ylim || xb1 + cs >= g.xlim) v = 0.f; }
-        return v;
     };
     // per-lane constants of the sampled outputs (self) / the skewed output pointers (stereo)
     int colb = -1, colbA2 = -1, colbB2 = -1;
@@ -159,55 +154,17 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
             if (hasB) outB[o] = vB;
         }
     };
-    auto wait_prev = [&](int need) {      // producer strip has published rows <= need (flag holds row + 1)
-        if (lane == 0) {
-            while (lf_ld_acquire(prog_prev) < need + 1) __nanosleep(64);
-        }
-        __syncwarp();
-    };
-
-    // ---- prologue: rows for the first-row formulas and for chunk 0 ----
+    // ---- prologue: source rows of chunk 0; the first row of the sums comes from k_sat_edges ----
     load_rows(lo, lo + 32 + k - 1);
     lf_cp_async_wait_all();
     __syncthreads();
 
     float curv[2] = { 0.f, 0.f }, prevv[2] = { 0.f, 0.f };
     if (hasplane) {
-        // first row of the strip (core:3345-3362 / :3530-3547): s(lo, j) = s(lo, j-1) + sum_p (d[lo+p][j-1+k] - d[lo+p][j-1]),
-        // the differences formed in parallel (lane p), the additions strictly in order
-        if (strip > 0) wait_prev(lo);
-        for (int pl = 0; pl < 2; ++pl) {
-            float left = 0.f, cur = 0.f, prevL = 0.f;
-            int l0 = 0;
-            if (strip == 0) {      // first patch: sequential sum over its k*k squared differences
-                float v = 0.0f;
-                for (int p = 0; p < k; ++p) {
-                    const float dv = lane < k ? dval(pl, lo + p, 1 + lane) : 0.f;
-                    for (int t = 0; t < k; ++t) v += __shfl_sync(FULL, dv, t);
-                }
-                left = v; l0 = 1;
-                if (lane == 0) cur = v;
-            } else {
-                left = __ldcg(&bnd_prev[lo + (pl ? bB : 0)]);
-                prevL = left;       // lane 0: s(lo, c0-1)
-            }
-            for (int l = l0; l <= lastlane; ++l) {
-                float s = left;
-                const float e = lane < k ? dval(pl, lo + lane, l + k) - dval(pl, lo + lane, l) : 0.f;
-                for (int t = 0; t < k; ++t) s += __shfl_sync(FULL, e, t);
-                if (lane == l) cur = s;
-                left = s;
-            }
-            const float up = __shfl_up_sync(FULL, cur, 1);
-            if (lane > 0) prevL = up;
-            curv[pl] = cur; prevv[pl] = prevL;
-        }
+        const float *frA = g.frow + (size_t) pid * w, *frB = g.frow + (size_t) (hasB ? pid + 1 : pid) * w;
+        if (j < g.col_end) { curv[0] = __ldg(frA + j); curv[1] = __ldg(frB + j); }
+        if (j - 1 >= lo && j - 1 < g.col_end) { prevv[0] = __ldg(frA + j - 1); prevv[1] = __ldg(frB + j - 1); }      // s(lo, j-1); lane 0 of strip 0: unused
         if (valid) emit(lo, curv[0], curv[1]);
-        if (has_next && lane == 31) {
-            __stcg(&bnd_next[lo], curv[0]);
-            if (hasB) __stcg(&bnd_next[lo + bB], curv[1]);
-            lf_st_release(prog_next, lo + 1);
-        }
     }
 
     // ---- wavefront over the remaining rows in chunks of 32 steps (core:3365-3387 / :3550-3572) ----
@@ -220,12 +177,16 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     unsigned ro1 = (unsigned) (((lo + 1 - lane - 1) & 127) * 256);
     unsigned ro2 = (unsigned) (((lo + 1 - lane - 1 + G.oy) & 127) * 256);
     const bool colz = SELF && (j + k - 1 >= g.xlim);
-    const bool skip0 = strip == 0 && lane == 0;
+    // lane 0 of strip 0 owns the first column of the plane: its sums come from k_sat_edges (through the same per-chunk staging the
+    // other strips use for the last column of their predecessor) and replace what the general recurrence would give
+    const bool lane0 = lane == 0;
+    const bool ovr = strip == 0 && lane0;
     // lane is active at steps s in [lane + 1, lane + Hh - 1]
-    const unsigned s_first = (valid && !skip0) ? (unsigned) (lane + 1) : 0x40000000u;
+    const unsigned s_first = valid ? (unsigned) (lane + 1) : 0x40000000u;
     const unsigned s_span = (unsigned) (Hh - 1);
     const bool bstore = has_next && lane == 31;
-    float *bpA = bnd_next + (lo - lane) + 1, *bpB = bpA + bB;       // running: bnd_next[i] of the current step
+    unsigned long long *bpA = bnd_next + (lo - lane) + 1, *bpB = bpA + bB;       // running: bnd_next[i] of the current step
+    unsigned btag = tag_hi | (unsigned) ((lo - lane + 1) & 0xffff);               // running: its tag
     float *opA = outA + 32, *opB = outB + 32;                       // running: skewed output slot of the current step
     // reference-row counters (self): phase and index of rows i and i + mir_di, advanced with the step
     int ph1 = 0, ai1 = 0, ph2 = 0, ai2 = 0;
@@ -257,6 +218,7 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
             nv = lf_sub2(nv, t2);
             nv = lf_sub2(nv, t3);
             nv = lf_add2(nv, t4);
+            if (ovr) nv = Lin2;
             prevL2 = Lin2;
             cur2 = nv;
             float vA, vB;
@@ -270,77 +232,152 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
                 *opA = vA;
                 if (hasB) *opB = vB;
             }
-            if (bstore) { __stcg(bpA, vA); if (hasB) __stcg(bpB, vB); }
+            if (bstore) {
+                lf_st_relaxed64(bpA, ((unsigned long long) btag << 32) | __float_as_uint(vA));
+                if (hasB) lf_st_relaxed64(bpB, ((unsigned long long) btag << 32) | __float_as_uint(vB));
+            }
         }
         ro1 = (ro1 + 256u) & 32767u;
         ro2 = (ro2 + 256u) & 32767u;
         ++bpA; ++bpB;
+        btag = tag_hi | ((btag + 1u) & 0xffffu);
         if (SELF) {
             if (++ph1 == g.gp) { ph1 = 0; ++ai1; }
             if (++ph2 == g.gp) { ph2 = 0; ++ai2; }
         } else { opA += 32; opB += 32; }
     };
-    // per-warp staging of the 32 boundary pairs of a chunk (strip > 0): lane 0 reads one pair per step
-    __shared__ unsigned long long s_bnd[SAT_NW][32];
-    const unsigned sbn = (unsigned) __cvta_generic_to_shared(&s_bnd[warp][0]);
-    // Boundary pairs of the producer strip are fetched one chunk ahead: its progress flag is read (acquire) during chunk q-1,
-    // the 32 pairs of chunk q+1 are requested at the start of chunk q if that value already covers them, and only a late
-    // producer makes the warp spin. The loads land while the chunk computes instead of in front of it.
-    auto bnd_rows = [&](int q) { return min(lo + 32 * q + 32, g.row_end - 1); };
-    auto bnd_load = [&](int q) -> unsigned long long {
-        const int r = lo + 32 * q + 1 + lane;
-        return r < g.row_end ? lf_pk(__ldcg(&bnd_prev[r]), __ldcg(&bnd_prev[r + bB])) : 0ull;
+    // Hand-off between the strips of a plane: lane 31 of the producer writes the sums of its last column as 64-bit (value, tag)
+    // words, tag = (launch epoch, row); the consumer stages the SAT_SUB pairs of its next sub-chunk of steps in shared memory (lane 0
+    // reads one pair per step), fetching them one sub-chunk ahead and re-reading only the words whose tag is not there yet. A
+    // 64-bit access is single-copy atomic: the matching tag guarantees the value, without flags or fences. A strip runs about
+    // 31 (skew of the wavefront) + 2 * SAT_SUB steps behind its predecessor. Strip 0 takes the plane's first column (k_sat_edges)
+    // through the same staging.
+    constexpr int SUB = SAT_SUB;
+    __shared__ unsigned long long s_bnd[SAT_NW][2][SUB];
+    const unsigned sbn = (unsigned) __cvta_generic_to_shared(&s_bnd[warp][0][0]);
+    const float *fcA = g.fcol + (size_t) pid * h, *fcB = fcA + (hasB ? (size_t) h : 0);
+    // boundary pair of this lane's row of sub-chunk v; *ok = both tags matched (spin: retry until they do)
+    auto sub_fetch = [&](int v, bool spin, bool *ok) -> unsigned long long {
+        const int r = lo + SUB * v + 1 + lane;
+        *ok = true;
+        if (lane >= SUB || r >= g.row_end) return 0ull;
+        if (strip == 0) return lf_pk(__ldg(fcA + r), __ldg(fcB + r));
+        const unsigned want = tag_hi | (unsigned) (r & 0xffff);
+        for (;;) {
+            const unsigned long long wa = lf_ld_relaxed64(bnd_prev + r), wb = lf_ld_relaxed64(bnd_prev + r + bB);
+            if ((unsigned) (wa >> 32) == want && (unsigned) (wb >> 32) == want)
+                return lf_pk(__uint_as_float((unsigned) wa), __uint_as_float((unsigned) wb));
+            if (!spin) { *ok = false; return 0ull; }
+            __nanosleep(20);
+        }
     };
-    // (not for the self variant with k = 16: at the 80-register cap of three CTAs per SM the extra state spills into its loop)
-    constexpr bool PREFETCH = !(SELF && K == 16);
     unsigned long long nb2 = 0ull;
     bool nb_have = false;
-    int prog_seen = (PREFETCH && hasplane && strip > 0) ? lf_ld_acquire(prog_prev) : 0;
+    const int nsub = (nsteps + SUB - 1) / SUB;
     for (int q = 0; q < nchunks; ++q) {
         // stage the source rows of the next chunk while this one runs
         load_rows(lo + 32 * (q + 1) + k, lo + 32 * (q + 1) + 32 + k - 1);
         if (hasplane) {
             const int send = min(32 * q + 32, nsteps);
-            if (strip > 0) {
-                if (!nb_have) { wait_prev(bnd_rows(q)); nb2 = bnd_load(q); }
-                s_bnd[warp][lane] = nb2;
+            for (int v = (32 / SUB) * q; v < (32 / SUB) * (q + 1) && SUB * v < send; ++v) {
+                const int s0 = SUB * v + 1, s1 = min(SUB * v + SUB, send);
+                bool ok;
+                if (!nb_have) nb2 = sub_fetch(v, true, &ok);
+                if (lane < SUB) s_bnd[warp][v & 1][lane] = nb2;
                 __syncwarp();
                 nb_have = false;
-                if (PREFETCH && q + 1 < nchunks) {
-                    if (prog_seen >= bnd_rows(q + 1) + 1) { nb2 = bnd_load(q + 1); nb_have = true; }
-                    prog_seen = lf_ld_acquire(prog_prev);
+                if (v + 1 < nsub) {      // one sub-chunk ahead, if the producer is already there
+                    nb2 = sub_fetch(v + 1, false, &ok);
+                    nb_have = __all_sync(FULL, ok);
                 }
-                unsigned bo = sbn;
-#pragma unroll (K == 8 ? 2 : 1)
-                for (int s = 32 * q + 1; s <= send; ++s, bo += 8) {
+                unsigned bo = sbn + (unsigned) (v & 1) * (SUB * 8);
+#pragma unroll 2
+                for (int s = s0; s <= s1; ++s, bo += 8) {
                     unsigned long long Lin2 = __shfl_up_sync(FULL, cur2, 1);
-                    if (lane == 0) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(Lin2) : "r"(bo));
+                    if (lane0) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(Lin2) : "r"(bo));
                     step_general(s, Lin2);
                 }
                 __syncwarp();
-            } else {
-                for (int s = 32 * q + 1; s <= send; ++s) {
-                    const unsigned long long Lsh2 = __shfl_up_sync(FULL, cur2, 1);
-                    // first column (core:3367-3372): differences by lanes q < k, additions in order by lane 0
-                    const int i0 = lo + s;
-                    if (i0 < g.row_end) {
-                        float cA, cB;
-                        lf_upk(cur2, cA, cB);
-                        float sumA = cA, sumB = cB;      // only lane 0's values are used
-                        const float eA = lane < k ? dval(0, i0 - 1 + k, 1 + lane) - dval(0, i0 - 1, 1 + lane) : 0.f;
-                        const float eB = lane < k ? dval(1, i0 - 1 + k, 1 + lane) - dval(1, i0 - 1, 1 + lane) : 0.f;
-                        for (int t = 0; t < k; ++t) { sumA += __shfl_sync(FULL, eA, t); sumB += __shfl_sync(FULL, eB, t); }
-                        if (lane == 0) { cur2 = lf_pk(sumA, sumB); emit(i0, sumA, sumB); }
-                    }
-                    step_general(s, Lsh2);
-                }
-            }
-            if (bstore) {      // rows <= lo + send - 31 of the last column are final
-                const int done = lo + send - 31;
-                if (done > lo) lf_st_release(prog_next, min(done, g.row_end - 1) + 1);
             }
         }
         lf_cp_async_wait_all();
+        __syncthreads();
+    }
+}
+
+// First row and first column of every plane's sums (core:3345-3372 / :3530-3557): the reference's dedicated formulas — the first
+// patch as a row-major running sum of its k*k squared differences, then per column j (row i) the running value plus the k
+// differences d[.][j-1+k] - d[.][j-1] (d[i-1+k][.] - d[i-1][.]) added strictly in order. These chains of W*k (H*k) dependent float
+// additions per plane cannot be shortened, but the planes are independent and the squared differences do not depend on the
+// running sums: one CTA per (group of planes sharing their source rows, direction); seven warps produce the squared differences
+// of the next 32 positions into shared memory (lanes <-> planes: neighbouring pixels) while lane p of warp 0 runs the chain of
+// plane p over the current 32. k_sat2 then starts every strip from these values instead of waiting for the strip to its left.
+#define SATE_NT 256
+#define SATE_B 32
+template <bool SELF, int K>
+__global__ void __launch_bounds__(SATE_NT) k_sat_edges(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
+                                                       float *__restrict__ frow, float *__restrict__ fcol)
+{
+    extern __shared__ float s_d[];                 // two buffers of [SATE_B + K][K][16] squared differences
+    constexpr int NA = SATE_B + K, BUF = NA * K * 16;
+    const SatGroup G = groups[blockIdx.x];
+    const int dir = blockIdx.y;                    // 0: first row (scan along x), 1: first column (scan along y)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int w = g.w, h = g.h, lo = g.lo;
+    const int end = dir == 0 ? g.col_end : g.row_end;
+    const int nblk = (end - lo - 1 + SATE_B - 1) / SATE_B;      // positions lo + 1 .. end - 1; at least one block (first patch)
+    const int pl = tid & 15;
+    const int ox = pl < G.nplanes ? planes[G.first_plane + pl].ox : 0;
+    const float *__restrict__ i1 = G.img1, *__restrict__ i2 = G.img2;
+    // squared differences of block b: along positions a0 .. a0 + NA - 1 (a0 = lo + b * SATE_B), across lo .. lo + K - 1
+    auto produce = [&](int b, int first_thread, int nthreads) {
+        float *D = s_d + (b & 1) * BUF;
+        const int a0 = lo + b * SATE_B;
+        for (int t = tid - first_thread; t < NA * K * 16; t += nthreads) {
+            const int ac = t >> 4, a = ac / K, c = ac - a * K;
+            if (pl >= G.nplanes) continue;
+            const int y = dir == 0 ? lo + c : a0 + a, x = dir == 0 ? a0 + a : lo + c;
+            float v = 0.f;
+            if (y < h) {       // pixels outside the image read as 0 (like the zero fill of k_sat2's row rings)
+                const float p1 = x < w ? __ldg(i1 + (size_t) y * w + x) : 0.f;
+                const int yy = y + G.oy, xx = x + ox;
+                const float p2 = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(i2 + (size_t) yy * w + xx) : 0.f;
+                const float df = p2 - p1;
+                v = df * df;
+                if (SELF) { if (y >= g.ylim || x >= g.xlim) v = 0.f; }
+            }
+            D[t] = v;
+        }
+    };
+    produce(0, 0, SATE_NT);
+    __syncthreads();
+    float s = 0.0f;
+    float *out = nullptr;
+    if (warp == 0 && lane < G.nplanes) {
+        const float *D = s_d;
+        // first patch: row-major over its k x k squared differences (p outer, t inner)
+        for (int p = 0; p < K; ++p)
+#pragma unroll
+            for (int t = 0; t < K; ++t) s += dir == 0 ? D[(t * K + p) * 16 + lane] : D[(p * K + t) * 16 + lane];
+        out = dir == 0 ? frow + (size_t) (G.first_plane + lane) * w : fcol + (size_t) (G.first_plane + lane) * h;
+        out[lo] = s;
+    }
+    for (int b = 0; b < nblk; ++b) {
+        if (warp == 0) {
+            if (lane < G.nplanes) {
+                const float *D = s_d + (b & 1) * BUF + lane;
+                const int p0 = lo + 1 + b * SATE_B;
+                const int np = min(SATE_B, end - p0);
+                for (int q = 0; q < np; ++q) {
+                    float e[K];
+#pragma unroll
+                    for (int c = 0; c < K; ++c) e[c] = D[((q + K) * K + c) * 16] - D[(q * K + c) * 16];
+#pragma unroll
+                    for (int c = 0; c < K; ++c) s += e[c];
+                    out[p0 + q] = s;
+                }
+            }
+        } else if (b + 1 < nblk) produce(b + 1, 32, SATE_NT - 32);
         __syncthreads();
     }
 }
@@ -502,7 +539,8 @@ struct SelGeom {
 
 // One warp selects the matches of reference patch r exactly like the reference (also under exact float ties).
 __device__ __forceinline__ void lf_bm_select_one(const SelGeom &g, const int r, unsigned long long *keys, const float *__restrict__ s_at,
-                                                 const float *__restrict__ s_mir, unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx)
+                                                 const float *__restrict__ s_mir, unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx,
+                                                 const PeerTable &pt)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -521,12 +559,12 @@ __device__ __forceinline__ void lf_bm_select_one(const SelGeom &g, const int r, 
             float test;
             if (rem <= nSim) {
                 const int ddk = djx + rem * Ns;
-                test = val = s_at[(size_t) ddk * g.R + r];
+                test = val = lf_peer_sum(pt, false, s_at, ddk, (size_t) g.R, r);
             } else {
                 const int a = nSim - (rem - nSim - 1);            // a = -di, di = -nSim + (rem - nSim - 1)
                 const int ddk = (Ns - 1 - djx) + a * Ns;
-                test = s_at[(size_t) ddk * g.R + r];
-                val = s_mir[(size_t) ddk * g.R + r];
+                test = lf_peer_sum(pt, false, s_at, ddk, (size_t) g.R, r);
+                val = lf_peer_sum(pt, true, s_mir, ddk, (size_t) g.R, r);
             }
             keep = test < g.threshold;
         }
@@ -631,12 +669,12 @@ __device__ __forceinline__ void lf_bm_select_one(const SelGeom &g, const int r, 
 // General path: one warp per reference patch, either all of them (list == nullptr) or the ones k_bm_select_fast deferred.
 __global__ void __launch_bounds__(32) k_bm_select(SelGeom g, const float *__restrict__ s_at, const float *__restrict__ s_mir,
                                                   unsigned *__restrict__ out_count, unsigned *__restrict__ out_idx,
-                                                  const unsigned *__restrict__ list, const unsigned *__restrict__ list_count)
+                                                  const unsigned *__restrict__ list, const unsigned *__restrict__ list_count, const PeerTable pt)
 {
     extern __shared__ unsigned long long keys[];      // up to Ns*Ns entries, later reused as LfPair[]
     const int n = list ? (int) *list_count : g.R;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        lf_bm_select_one(g, list ? (int) list[i] : i, keys, s_at, s_mir, out_count, out_idx);
+        lf_bm_select_one(g, list ? (int) list[i] : i, keys, s_at, s_mir, out_count, out_idx, pt);
         __syncwarp();
     }
 }

@@ -40,6 +40,24 @@ struct LfTables {
 
 __constant__ LfTables c_tab;
 
+// Multi-GPU team path: where the sampled self sums of every offset plane live (rank q holds the planes pl0[q] .. pl0[q+1]-1 in ITS
+// s_at / s_mir, reached through peer pointers: NVLink loads), for the reference patches whose selection needs the complete candidate
+// sequence (exact distance ties).
+#define LF_MAXRANKS 16
+struct PeerTable {
+    const float *s_at[LF_MAXRANKS];
+    const float *s_mir[LF_MAXRANKS];
+    int pl0[LF_MAXRANKS + 1];
+    int G;                        // 0: no table, everything is local
+};
+__device__ __forceinline__ float lf_peer_sum(const PeerTable &pt, bool mir, const float *local, int ddk, size_t R, int r)
+{
+    if (pt.G == 0) return local[(size_t) ddk * R + r];
+    int q = 0;
+    while (q + 1 < pt.G && ddk >= pt.pl0[q + 1]) ++q;
+    return (mir ? pt.s_mir[q] : pt.s_at[q])[(size_t) ddk * R + r];
+}
+
 struct LfWindow {
     int      st[LF_MAXA];        // global SAI index of each window slot
     unsigned mask[LF_MAXA];
@@ -98,10 +116,31 @@ __device__ __forceinline__ unsigned long long lf_fma2(unsigned long long a, unsi
     return r;
 }
 
+// 64-bit (value, tag) words handed from CTA to CTA through L2: a naturally aligned 64-bit access is single-copy atomic, so a
+// consumer that finds the tag it expects also has the value that was written with it — no flag, no fence
+__device__ __forceinline__ void lf_st_relaxed64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lf_ld_relaxed64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // release/acquire flag accesses at GPU scope (producer/consumer hand-off between CTAs)
 __device__ __forceinline__ void lf_st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+// polling load: strong at GPU scope (served by L2) but without the L1 invalidation an acquire load carries (CCTL.IVALL on sm_100);
+// spin on this one, then read the flag once more with lf_ld_acquire before touching the data it guards
+__device__ __forceinline__ int lf_ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ int lf_ld_acquire(const int *p)
 {

@@ -160,10 +160,11 @@ struct lfbm5d_ctx {
     DevBuf noisy, basic, out, num, den, mask;
     DevBuf nsym, bsym, numsym, densym, est0;
     DevBuf s_at, s_mir, sums, first, shape, bmcount, bmidx, satgroups, satplanes, bnd, progress, rowmap, colmap, rows, cols, counters,
-           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist, act, rt_noisy, rt_basic;
+           zbuf, wbuf, spos, gflag, arange, brange, gmask, shape_lut, tielist, stielist, act, rt_noisy, rt_basic, frow, fcol;
     unsigned lut_asw = 0;
     lfbm5d_stats stats{};
     bool timing = false;
+    unsigned sat_epoch = 0;        // pass counter (16 bits): tags the strip hand-off words of k_sat2
     bool bm_only = false;          // lfbm5d_debug_block_matching: a pass stops behind the match tables
     cudaEvent_t ev[5]{};
     unsigned max_passes = 0;
@@ -378,7 +379,12 @@ int ensure_pass_buffers(lfbm5d_ctx *ctx, const PassCfg &pc)
     if (ctx->bmcount.ensure(R * 4) || ctx->bmidx.ensure(R * (pc.N + 1) * 4)) return 1;
     const size_t nplanes = nself + (pc.A - 1) * Nd * Nd;
     const size_t max_strips = std::max(st_strips, (size_t) (pc.wb - 2 * pc.n + 31) / 32);
-    if (ctx->bnd.ensure(nplanes * max_strips * pc.hb * 4) || ctx->progress.ensure((nplanes * max_strips + 4) * 4)) return 1;
+    {   // hand-off words of k_sat2: a fresh buffer holds no valid tag (epochs start at 1)
+        const void *before = ctx->bnd.p;
+        if (ctx->bnd.ensure(nplanes * max_strips * pc.hb * 8) || ctx->progress.ensure(64)) return 1;
+        if (ctx->bnd.p != before) CK(cudaMemsetAsync(ctx->bnd.p, 0, ctx->bnd.cap, ctx->stream));
+    }
+    if (ctx->frow.ensure(nplanes * pc.wb * 4) || ctx->fcol.ensure(nplanes * pc.hb * 4)) return 1;
     if (ctx->counters.ensure(64 * 8)) return 1;
     if (ctx->zbuf.ensure(R * pc.N * pc.A * pc.C * pc.k * pc.k * 4) || ctx->wbuf.ensure(R * pc.C * 4) ||
         ctx->spos.ensure(R * pc.N * pc.A * 4)) return 1;
@@ -535,13 +541,27 @@ SatPlan *sat_plan(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int p
     return ctx->sat_cache.back().get();
 }
 
+// New pass: reset the two ticket counters and move on to the next epoch of the hand-off tags (1 .. 65535; when the counter wraps the
+// words are cleared, so that a word written 65535 passes ago under another geometry can never be taken for a fresh one)
+int next_sat_epoch(lfbm5d_ctx *ctx)
+{
+    CK(cudaMemsetAsync(ctx->progress.p, 0, 16, ctx->stream));
+    if (++ctx->sat_epoch > 0xffffu) {
+        ctx->sat_epoch = 1;
+        CK(cudaStreamSynchronize(ctx->stream3));
+        CK(cudaMemsetAsync(ctx->bnd.p, 0, ctx->bnd.cap, ctx->stream));
+    }
+    return 0;
+}
+
 // Summed-area planes of the self groups [sg0, sg1) on `strm` (ticket counter 0) ...
 int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg0, int sg1, cudaStream_t strm)
 {
     if (sg1 <= sg0) return 0;
     const PassGeom pg = pass_geom(pc);
-    int *ticket = ctx->progress.as<int>(), *flags = ticket + 4;
+    int *ticket = ctx->progress.as<int>();
     SatGeom g{};
+    g.epoch = ctx->sat_epoch;
     g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = pc.n; g.row_end = P.self_row_end; g.col_end = P.self_col_end;
     g.ylim = pc.hb - pc.n; g.xlim = pc.wb - pc.n; g.nstrips = P.self_strips; g.pstrips = P.pstrips; g.SR = 0;
     g.nc = pg.nc; g.rowmap = ctx->rowmap.as<int>(); g.colmap = ctx->colmap.as<int>();
@@ -549,11 +569,17 @@ int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg
     g.nreg = 0;      // rows produced by the regular stride of ind_initialize (utilities.cpp:697-712)
     for (unsigned ind = pc.n; ind < pc.hb - pc.k + 1 - pc.n; ind += pc.p) g.nreg++;
     g.negzero2 = 0x8000000080000000ull;
+    g.frow = ctx->frow.as<float>(); g.fcol = ctx->fcol.as<float>();
     const size_t smem = 2 * (128 + pc.k) * 64 * 4;
     auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
+    auto kedge = pc.k == 8 ? k_sat_edges<true, 8> : k_sat_edges<true, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t smem_e = (size_t) 2 * (SATE_B + pc.k) * pc.k * 16 * 4;
+    CK(cudaFuncSetAttribute((const void *) kedge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_e));
+    kedge<<<dim3(sg1 - sg0, 2), SATE_NT, smem_e, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), ctx->frow.as<float>(), ctx->fcol.as<float>());
+    ctx->stats.kernel_launches++;
     kfn<<<(sg1 - sg0) * P.self_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), sg1 - sg0,
-                                                                  ctx->bnd.as<float>(), flags, ticket);
+                                                                  ctx->bnd.as<unsigned long long>(), ticket);
     ctx->stats.kernel_launches++;
     return 0;
 }
@@ -561,17 +587,25 @@ int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg
 int launch_sat_stereo(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int s0, int s1, cudaStream_t strm)
 {
     if (s1 <= s0) return 0;
-    int *ticket = ctx->progress.as<int>(), *flags = ticket + 4;
+    int *ticket = ctx->progress.as<int>();
     SatGeom g{};
+    g.epoch = ctx->sat_epoch;
     g.w = pc.wb; g.h = pc.hb; g.k = pc.k; g.lo = P.st_lo; g.row_end = P.st_row_end; g.col_end = P.st_col_end;
     g.ylim = pc.hb; g.xlim = pc.wb; g.nstrips = P.st_strips; g.pstrips = P.pstrips; g.SR = P.st_SR;
     g.gp = 1; g.negzero2 = 0x8000000080000000ull;
+    g.frow = ctx->frow.as<float>(); g.fcol = ctx->fcol.as<float>();
     const size_t smem = 2 * (128 + pc.k) * 64 * 4;
     const int ngroups = (s1 - s0) * P.groups_per_slot;
     auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
+    auto kedge = pc.k == 8 ? k_sat_edges<false, 8> : k_sat_edges<false, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const size_t smem_e = (size_t) 2 * (SATE_B + pc.k) * pc.k * 16 * 4;
+    CK(cudaFuncSetAttribute((const void *) kedge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_e));
+    kedge<<<dim3(ngroups, 2), SATE_NT, smem_e, strm>>>(g, P.d_groups.as<SatGroup>() + P.nself_groups + s0 * P.groups_per_slot, P.d_planes.as<SatPlane>(),
+                                                       ctx->frow.as<float>(), ctx->fcol.as<float>());
+    ctx->stats.kernel_launches++;
     kfn<<<ngroups * P.st_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + P.nself_groups + s0 * P.groups_per_slot,
-                                                            P.d_planes.as<SatPlane>(), ngroups, ctx->bnd.as<float>(), flags, ticket + 1);
+                                                            P.d_planes.as<SatPlane>(), ngroups, ctx->bnd.as<unsigned long long>(), ticket + 1);
     ctx->stats.kernel_launches++;
     return 0;
 }
@@ -601,10 +635,10 @@ int launch_self_select(lfbm5d_ctx *ctx, const PassCfg &pc, cudaStream_t strm)
         LAUNCH_ON(ctx, strm, kfast, (R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(),
                   ctx->bmidx.as<unsigned>(), tl, tl + R);
         LAUNCH_ON(ctx, strm, k_bm_select, std::min<size_t>(R, (size_t) ctx->num_sms * 16), 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(),
-                  ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl, (const unsigned *) (tl + R));
+                  ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl, (const unsigned *) (tl + R), PeerTable{});
     } else
         LAUNCH_ON(ctx, strm, k_bm_select, R, 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(),
-                  ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) nullptr, (const unsigned *) nullptr);
+                  ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) nullptr, (const unsigned *) nullptr, PeerTable{});
     return 0;
 }
 
@@ -751,7 +785,7 @@ int run_pass(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int pst, i
     SatPlan *Pp = sat_plan(ctx, pc, win, pst, partial, act_ymax, act_xmax);
     if (!Pp) return 1;
     const SatPlan &P = *Pp;
-    CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + P.planes.size() * (size_t) P.pstrips) * 4, ctx->stream));
+    if (next_sat_epoch(ctx)) return 1;
     cudaEvent_t sat0 = ctx->ev[2], sat1 = ctx->ev[3];
     if (ctx->timing) CK(cudaEventRecord(sat0, ctx->stream));
     // Self matching (summed-area planes, selection) stays on the main stream; disparity matching (planes, argmin, ties) runs
@@ -1204,7 +1238,7 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     DevBuf *all[] = { &ctx->noisy, &ctx->basic, &ctx->out, &ctx->num, &ctx->den, &ctx->mask, &ctx->nsym, &ctx->bsym, &ctx->numsym,
                       &ctx->densym, &ctx->est0, &ctx->s_at, &ctx->s_mir, &ctx->sums, &ctx->first, &ctx->shape, &ctx->bmcount,
                       &ctx->bmidx, &ctx->satgroups, &ctx->satplanes, &ctx->bnd, &ctx->progress, &ctx->rowmap, &ctx->colmap, &ctx->rows, &ctx->cols, &ctx->counters,
-                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act, &ctx->rt_noisy, &ctx->rt_basic };
+                      &ctx->zbuf, &ctx->wbuf, &ctx->spos, &ctx->gflag, &ctx->arange, &ctx->brange, &ctx->gmask, &ctx->shape_lut, &ctx->tielist, &ctx->stielist, &ctx->act, &ctx->rt_noisy, &ctx->rt_basic, &ctx->frow, &ctx->fcol };
     for (auto b : all) b->release();
     for (auto &e : ctx->sat_cache) { e->d_planes.release(); e->d_groups.release(); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);

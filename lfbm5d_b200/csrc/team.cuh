@@ -85,6 +85,16 @@ struct lfbm5d_team {
     std::vector<float *> d_noisy, d_basic; // per local rank
     unsigned long long bytes_exchanged = 0;
     unsigned passes_redone = 0;
+    // peer view of the sampled self sums (exact-tie selection): per rank the device pointers of its s_at / s_mir as seen from
+    // here (emulated: the other contexts' buffers; NCCL: cudaIpc mappings over NVLink)
+    bool peer_ready = false, peer_ok = true;
+    const float *peer_at[LF_MAXRANKS] = {}, *peer_mir[LF_MAXRANKS] = {};
+    bool peer_open[LF_MAXRANKS] = {};
+    unsigned long long tie_patches = 0;
+    // per-phase device time of local rank 0 (lfbm5d_team_timing): events at the phase boundaries of a pass
+    bool timing = false;
+    cudaEvent_t tev[12] = {}, bev[6] = {};
+    float phase_ms[12] = {};
 };
 
 namespace {
@@ -245,6 +255,8 @@ int team_ensure(lfbm5d_team *T, lfbm5d_ctx *ctx, const PassCfg &pc)
     return 0;
 }
 
+#define TMARK(i) do { if (T->timing) CK(cudaEventRecord(T->tev[i], T->local[0]->stream)); } while (0)
+
 // ---- one core call of the team (all ranks in lockstep; `pst == cst` or the partial-window branch) ----
 // Returns through *cov the number of covered entries of LF_denoised_percent (summed over the ranks).
 int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, int cst, unsigned long long *cov)
@@ -256,6 +268,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
     const int C = (int) pc.C, wb = (int) pc.wb;
     std::vector<SatPlan *> plans(nl);
     std::vector<PlaneShare> share;
+    TMARK(2);
     // ---- block matching: own planes ----
     for (int l = 0; l < nl; l++) {
         lfbm5d_ctx *ctx = T->local[l];
@@ -272,16 +285,20 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
         const SatPlan &P = *Pp;
         if (share.empty()) share = team_planes(P, G);
         const PlaneShare &sh = share[g];
-        CK(cudaMemsetAsync(ctx->progress.p, 0, (4 + P.planes.size() * (size_t) P.pstrips) * 4, ctx->stream));
+        if (next_sat_epoch(ctx)) return 1;
         cudaStream_t sB = ctx->stream3;
         CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
         CK(cudaStreamWaitEvent(sB, ctx->ev_fork, 0));
+        const bool tm = T->timing && l == 0;
+        if (tm) CK(cudaEventRecord(T->bev[0], ctx->stream));
         if (launch_sat_stereo(ctx, pc, P, sh.s0, sh.s1, sB)) return 1;
+        if (tm) CK(cudaEventRecord(T->bev[3], sB));
         if (pg.nself > 0 && sh.pl1 > sh.pl0) {
             LAUNCH(ctx, k_fill, grid_for(ctx, (size_t) (sh.pl1 - sh.pl0) * pg.R), 256, 0, ctx->s_mir.as<float>() + (size_t) sh.pl0 * pg.R, 2 * pg.threshold,
                    (size_t) (sh.pl1 - sh.pl0) * pg.R);   // core:3317
             if (launch_sat_self(ctx, pc, P, sh.sg0, sh.sg1, ctx->stream)) return 1;
         }
+        if (tm) CK(cudaEventRecord(T->bev[1], ctx->stream));
         if (pg.nself > 0) {
             SelGeom sg{};
             sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
@@ -298,11 +315,16 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             LAUNCH(ctx, kp, (pg.R + 127) / 128, 128, 0, sg, ctx->s_at.as<float>(), ctx->s_mir.as<float>(), sh.pl0, sh.pl1, b->pcnt_send.as<unsigned>(),
                    b->pkey_send.as<unsigned long long>());
         }
+        if (tm) CK(cudaEventRecord(T->bev[2], ctx->stream));
         if (launch_stereo_argmin(ctx, pc, P, sh.s0, sh.s1, sB)) return 1;
+        if (tm) CK(cudaEventRecord(T->bev[4], sB));
         CK(cudaEventRecord(ctx->ev_join, sB));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        if (tm) CK(cudaEventRecord(T->tev[3], ctx->stream));
+        if (!T->comm && T->timing) CK(cudaDeviceSynchronize());      // emulated team under timing: one rank at a time on the device
     }
     const SatPlan &P0 = *plans[0];
+    if (T->comm) TMARK(3);
     {   // ---- exchange: disparity maps to everybody, partial candidate lists to the owners of the reference rows ----
         std::vector<TeamSeg> segs;
         for (int g = 0; g < G; g++)
@@ -323,6 +345,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
     }
     bool redo = false;
     for (int attempt = 0; attempt < 2; attempt++) {
+        TMARK(4);
         // ---- merged selection, groups and the first part of the aggregation: rows [pc1, c1) ----
         for (int l = 0; l < nl; l++) {
             lfbm5d_ctx *ctx = T->local[l];
@@ -338,7 +361,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                     SelGeom sg{};
                     sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
                     sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
-                    void (*km)(SelGeom, int, int, int, const unsigned *, const unsigned long long *, unsigned *, unsigned *, unsigned *) = nullptr;
+                    void (*km)(SelGeom, int, int, int, const unsigned *, const unsigned long long *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
                     switch (pc.N) {
                         case 2: km = k_bm_merge<3>; break;
                         case 4: km = k_bm_merge<5>; break;
@@ -346,8 +369,22 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                         case 16: km = k_bm_merge<17>; break;
                         default: km = k_bm_merge<33>; break;
                     }
+                    if (ctx->tielist.ensure(((size_t) pg.R + 1) * 4)) return 1;
+                    unsigned *tl = ctx->tielist.as<unsigned>();
+                    // with the peer view the tied patches are redone right here; without it they are only counted (cnts[1]) and the
+                    // team falls back to exchanging the complete sums and redoing the pass
+                    unsigned *tcount = T->peer_ready ? reinterpret_cast<unsigned *>(cnts + 2) : reinterpret_cast<unsigned *>(cnts + 1);
                     LAUNCH(ctx, km, (nown + 127) / 128, 128, 0, sg, G, bd.r0, bd.r1, b->pcnt_all.as<unsigned>(), b->pkey_all.as<unsigned long long>(),
-                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), reinterpret_cast<unsigned *>(cnts + 1));
+                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), T->peer_ready ? tl : (unsigned *) nullptr, tcount);
+                    if (T->peer_ready) {
+                        PeerTable pt{};
+                        pt.G = G;
+                        for (int q = 0; q < G; q++) { pt.s_at[q] = T->peer_at[q]; pt.s_mir[q] = T->peer_mir[q]; pt.pl0[q] = share[q].pl0; }
+                        pt.pl0[G] = share[G - 1].pl1;
+                        LAUNCH(ctx, k_bm_select, std::min<size_t>(nown, (size_t) ctx->num_sms * 16), 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(),
+                               ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl,
+                               (const unsigned *) reinterpret_cast<unsigned *>(cnts + 2), pt);
+                    }
                 } else if (pg.nself > 0) {      // ties somewhere: every rank now holds the complete sums, the reference's selection as on one GPU
                     if (launch_self_select(ctx, pc, ctx->stream)) return 1;
                 } else
@@ -360,6 +397,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                 if (launch_aggregate(ctx, pc, win, bd.pc1, bd.c1, bd.a0, bd.a1)) return 1;
             }
         }
+        TMARK(5);
         {   // rows O_g = [y1, c1) go to the next rank, which continues the sums
             std::vector<TeamSeg> segs;
             for (int g = 0; g + 1 < G; g++) {
@@ -376,6 +414,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             }
             if (team_exchange(T, segs)) return 1;
         }
+        TMARK(6);
         // ---- second part of the aggregation: rows [y0, pc1) on top of the previous rank's sums; coverage and tie counts ----
         for (int l = 0; l < nl; l++) {
             lfbm5d_ctx *ctx = T->local[l];
@@ -389,6 +428,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                 LAUNCH(ctx, k_count_cov_rows, grid_for(ctx, (size_t) pc.A * C * (bd.i1 - bd.i0) * pc.W), 256, 0, ctx->densym.as<float>(), win, (int) pc.W, (int) pc.H,
                        C, (int) pc.n, (int) pc.k, bd.i0, bd.i1 - bd.i0, cnts);
         }
+        TMARK(7);
         {   // final rows [y0, pc1) back to the previous rank (its replica of O_{g-1}); counters to everybody
             std::vector<TeamSeg> segs;
             for (int g = 1; g < G; g++) {
@@ -403,9 +443,10 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                     }
                 }
             }
-            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, 16 });
+            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, 24 });
             if (team_exchange(T, segs)) return 1;
         }
+        TMARK(8);
         // ---- every rank reads the same counters and takes the same decision ----
         unsigned long long total_cov = 0, total_ties = 0;
         for (int l = 0; l < nl; l++) {
@@ -414,10 +455,20 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             std::vector<unsigned long long> h((size_t) G * 64);
             CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
-            if (l == 0) for (int g = 0; g < G; g++) { total_cov += h[(size_t) g * 64]; total_ties += h[(size_t) g * 64 + 1] & 0xffffffffull; }
+            if (l == 0)
+                for (int g = 0; g < G; g++) {
+                    total_cov += h[(size_t) g * 64]; total_ties += h[(size_t) g * 64 + 1] & 0xffffffffull;
+                    T->tie_patches += h[(size_t) g * 64 + 2] & 0xffffffffull;
+                }
             ctx->stats.window_passes++;
         }
         *cov = total_cov;
+        if (T->timing) {    // phases 2..8: block matching, exchange, selection + groups + aggregation, exchange, aggregation 2, exchange
+            for (int i = 2; i < 8; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
+            // inside block matching: self planes, partial selection (main stream); disparity planes, argmin (second stream)
+            const int pairs[4][2] = { { 0, 1 }, { 1, 2 }, { 0, 3 }, { 3, 4 } };
+            for (int i = 0; i < 4; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->bev[pairs[i][0]], T->bev[pairs[i][1]]) == cudaSuccess) T->phase_ms[8 + i] += ms; }
+        }
         if (total_ties == 0 || redo) break;
         // Exact float ties among the selected distances of some reference patch: the reference's result then depends on its heap
         // algorithm over the complete candidate sequence. Redo the pass from the padded accumulators with the complete sums on
@@ -500,6 +551,102 @@ int team_count_zero(lfbm5d_team *T, const std::vector<int> &items, bool padded, 
     return 0;
 }
 
+// tiny all-to-all of host values through the counter slots (also a barrier: a rank has everybody's value only after everybody
+// reached this point): slot g = 64 x 8 bytes
+int team_host_allgather(lfbm5d_team *T, const void *mine_per_local, size_t bytes, std::vector<unsigned char> &all)
+{
+    const int G = T->world, nl = (int) T->local.size();
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        CK(cudaSetDevice(ctx->device));
+        TeamCtxBufs *b = team_bufs(ctx);
+        if (b->counters.ensure((size_t) G * 64 * 8 + 64)) return 1;
+        CK(cudaMemcpyAsync(b->counters.as<char>() + (size_t) T->local_rank[l] * 512, (const char *) mine_per_local + (size_t) l * bytes, bytes,
+                           cudaMemcpyHostToDevice, ctx->stream));
+    }
+    std::vector<TeamSeg> segs;
+    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 512, (size_t) g * 512, bytes });
+    if (team_exchange(T, segs)) return 1;
+    all.assign((size_t) G * bytes, 0);
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        CK(cudaSetDevice(ctx->device));
+        std::vector<unsigned char> h((size_t) G * 512);
+        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (l == 0) for (int g = 0; g < G; g++) memcpy(all.data() + (size_t) g * bytes, h.data() + (size_t) g * 512, bytes);
+    }
+    return 0;
+}
+
+void team_peer_close(lfbm5d_team *T)
+{
+    for (int g = 0; g < LF_MAXRANKS; g++)
+        if (T->peer_open[g]) {
+            cudaIpcCloseMemHandle(const_cast<float *>(T->peer_at[g]));
+            cudaIpcCloseMemHandle(const_cast<float *>(T->peer_mir[g]));
+            T->peer_open[g] = false;
+        }
+    T->peer_ready = false;
+}
+
+// Make the self sums of every rank addressable from every rank. s_at / s_mir are (re)allocated here, with all peer mappings closed
+// first (an exported allocation must not be freed while it is mapped elsewhere), then exported / imported again.
+int team_peer_setup(lfbm5d_team *T, const PassCfg &pc)
+{
+    const PassGeom pg = pass_geom(pc);
+    const int G = T->world, nl = (int) T->local.size();
+    const size_t need = (size_t) pg.nself * pg.R * 4;
+    if (need == 0) return 0;
+    if (!T->comm) {      // emulated: all contexts live here
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            CK(cudaSetDevice(ctx->device));
+            if (ctx->s_at.ensure(need) || ctx->s_mir.ensure(need)) return 1;
+        }
+        for (int l = 0; l < nl; l++) { T->peer_at[T->local_rank[l]] = T->local[l]->s_at.as<float>(); T->peer_mir[T->local_rank[l]] = T->local[l]->s_mir.as<float>(); }
+        T->peer_ready = T->peer_ok;
+        return 0;
+    }
+    lfbm5d_ctx *ctx = T->local[0];
+    const int me = T->local_rank[0];
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long flag = (need > ctx->s_at.cap || need > ctx->s_mir.cap || !T->peer_ready) ? 1 : 0;
+    std::vector<unsigned char> all;
+    if (team_host_allgather(T, &flag, 8, all)) return 1;
+    bool any = false;
+    for (int g = 0; g < G; g++) any = any || *reinterpret_cast<unsigned long long *>(all.data() + (size_t) g * 8) != 0;
+    if (!any) return 0;
+    team_peer_close(T);
+    if (team_host_allgather(T, &flag, 8, all)) return 1;        // barrier: every mapping is closed before anybody frees
+    const size_t want = need + need / 8;                          // some room: the next step's grid may be a little larger
+    if (need > ctx->s_at.cap && ctx->s_at.ensure(want)) return 1;
+    if (need > ctx->s_mir.cap && ctx->s_mir.ensure(want)) return 1;
+    struct { cudaIpcMemHandle_t at, mir; unsigned long long ok; } mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.ok = T->peer_ok && cudaIpcGetMemHandle(&mine.at, ctx->s_at.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.mir, ctx->s_mir.p) == cudaSuccess;
+    cudaGetLastError();
+    if (team_host_allgather(T, &mine, sizeof(mine), all)) return 1;
+    bool ok = true;
+    for (int g = 0; g < G; g++) ok = ok && reinterpret_cast<decltype(mine) *>(all.data() + (size_t) g * sizeof(mine))->ok != 0;
+    if (ok)
+        for (int g = 0; g < G && ok; g++) {
+            if (g == me) { T->peer_at[g] = ctx->s_at.as<float>(); T->peer_mir[g] = ctx->s_mir.as<float>(); continue; }
+            auto *h = reinterpret_cast<decltype(mine) *>(all.data() + (size_t) g * sizeof(mine));
+            void *pa = nullptr, *pm = nullptr;
+            if (cudaIpcOpenMemHandle(&pa, h->at, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pm, h->mir, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); if (pa) cudaIpcCloseMemHandle(pa); break; }
+            T->peer_at[g] = (const float *) pa; T->peer_mir[g] = (const float *) pm; T->peer_open[g] = true;
+        }
+    // everybody must agree (a rank that could not map its peers makes the whole team take the exchange-based fallback)
+    unsigned long long okf = ok ? 1 : 0;
+    if (team_host_allgather(T, &okf, 8, all)) return 1;
+    for (int g = 0; g < G; g++) ok = ok && *reinterpret_cast<unsigned long long *>(all.data() + (size_t) g * 8) != 0;
+    if (!ok) { team_peer_close(T); T->peer_ok = false; }
+    T->peer_ready = ok;
+    return 0;
+}
+
 int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *const *d_noisy, float *const *d_basic, const unsigned *mask_)
 {
     if (validate(p_, step)) return 1;
@@ -543,6 +690,11 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
         }
         CK(cudaMemsetAsync(ctx->num.p, 0, asize * each * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
+    }
+    if (team_peer_setup(T, S.pc)) return 1;       // (re)allocates s_at / s_mir under the export protocol, before ensure_pass_buffers sees them
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        CK(cudaSetDevice(ctx->device));
         if (setup_tables(ctx, step, p, S.tau_4D) || ensure_pass_buffers(ctx, S.pc) || upload_grid(ctx, S.pc) || team_ensure(T, ctx, S.pc)) return 1;
     }
     return 0;
@@ -609,6 +761,7 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
         for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); if (setup_tables(T->local[l], step, p, S.tau_4D)) return 1; }
         S.tables_tau4 = S.tau_4D;
     }
+    TMARK(0);
     for (int l = 0; l < nl; l++) {      // padded working set on the rows the own groups touch; running estimate on them as well
         lfbm5d_ctx *ctx = T->local[l];
         const Band &bd = T->bands[T->local_rank[l]];
@@ -643,9 +796,12 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
                     LAUNCH(ctx, k_est0_rows, grid_for(ctx, (size_t) Aw * (bd.y1 - bd.y0) * pc.wb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
                            ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.wb, (int) pc.hb, (int) C, bd.y0, bd.y1 - bd.y0);
             }
+        TMARK(1);
         if (team_est0_exchange(T, pc, win)) return 1;
         unsigned long long cnt = 0;
         if (team_pass(T, pc, win, (int) pst_asw, (int) cst_asw, &cnt)) return 1;
+        if (T->timing && calls == 0)
+            for (int i = 0; i < 2; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
         calls++;
         win.proc[pst_asw] += 1;
         S.proc[win.st[pst_asw]] += 1;
@@ -752,7 +908,7 @@ extern "C" {
 
 int lfbm5d_team_create_emulated(lfbm5d_team **out, int device, int world)
 {
-    if (!out || world < 1 || world > 64) return fail("bad team arguments");
+    if (!out || world < 1 || world > LF_MAXRANKS) return fail("bad team arguments (1 <= world <= 16)");
     lfbm5d_team *T = new lfbm5d_team();
     T->world = world; T->owns_ctx = true;
     for (int g = 0; g < world; g++) {
@@ -776,7 +932,7 @@ int lfbm5d_team_unique_id(char *id128)
 
 int lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int world, const char *id128)
 {
-    if (!out || !ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail("bad team arguments");
+    if (!out || !ctx || !id128 || world < 1 || world > LF_MAXRANKS || rank < 0 || rank >= world) return fail("bad team arguments (1 <= world <= 16)");
     if (nccl_load()) return 1;
     CK(cudaSetDevice(ctx->device));
     lfbm5d_team *T = new lfbm5d_team();
@@ -793,7 +949,14 @@ int lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int wo
 void lfbm5d_team_destroy(lfbm5d_team *T)
 {
     if (!T) return;
-    for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); team_bufs_release(c); }
+    for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    if (T->comm && T->peer_ready) {      // nobody frees its sums while they are mapped elsewhere
+        team_peer_close(T);
+        unsigned long long z = 0;
+        std::vector<unsigned char> all;
+        team_host_allgather(T, &z, 8, all);
+    }
+    for (auto c : T->local) team_bufs_release(c);
     if (T->comm) g_nccl.CommDestroy(T->comm);
     if (T->owns_ctx) for (auto c : T->local) lfbm5d_destroy(c);
     delete T;
@@ -830,11 +993,76 @@ int lfbm5d_team_band(lfbm5d_team *T, int rank, int *row_lo, int *row_hi, int *ke
     return 0;
 }
 
-void lfbm5d_team_stats(lfbm5d_team *T, unsigned long long *bytes_exchanged, unsigned *passes_redone)
+/* Bands a step with parameters p would use on a team of `world` ranks, without running it: interior rows [*row_lo, *row_hi) owned by
+ * `rank`, and [*row_lo, *keep_hi) = every row of the inputs the rank reads (what a host driver has to upload to it). */
+int lfbm5d_team_plan_band(int world, int rank, int step, const lfbm5d_params *p, int *row_lo, int *row_hi, int *keep_hi)
+{
+    if (!p || world < 1 || world > LF_MAXRANKS || rank < 0 || rank >= world) return fail("bad arguments");
+    if (validate(p, step)) return 1;
+    PassCfg pc;
+    if (make_passcfg(pc, step, p, p->tau_4D)) return 1;
+    const std::vector<Band> B = team_bands(pc, world);
+    if (row_lo) *row_lo = B[rank].i0;
+    if (row_hi) *row_hi = B[rank].i1;
+    if (keep_hi) *keep_hi = B[rank].j1;
+    return 0;
+}
+
+/* Copy the rows [row_lo, row_hi) of every plane of every non-masked SAI between caller-owned host arrays (asize pointers, planar
+ * width*height*chnls floats each, as for lfbm5d_step1) and a device light field [asize][chnls][height][width], on the context's
+ * stream (asynchronous: pinned host memory makes it overlap; lfbm5d_sync waits). One strided copy per SAI. */
+int lfbm5d_copy_rows(lfbm5d_ctx *ctx, float *const *host, float *d_lf, const unsigned *sai_mask, unsigned asize, unsigned chnls, unsigned width,
+                     unsigned height, unsigned row_lo, unsigned row_hi, int to_device)
+{
+    if (!ctx || !host || !d_lf || !sai_mask) return fail("null argument");
+    if (row_hi > height || row_lo >= row_hi) return row_lo == row_hi ? 0 : fail("bad row range");
+    CK(cudaSetDevice(ctx->device));
+    const size_t plane = (size_t) width * height, rowbytes = (size_t) (row_hi - row_lo) * width * 4;
+    for (unsigned st = 0; st < asize; st++) {
+        if (!sai_mask[st]) continue;
+        float *d = d_lf + (size_t) st * chnls * plane + (size_t) row_lo * width;
+        float *hp = host[st] + (size_t) row_lo * width;
+        if (to_device) CK(cudaMemcpy2DAsync(d, plane * 4, hp, plane * 4, rowbytes, chnls, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemcpy2DAsync(hp, plane * 4, d, plane * 4, rowbytes, chnls, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return 0;
+}
+
+int lfbm5d_sync(lfbm5d_ctx *ctx)
+{
+    if (!ctx) return fail("null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void lfbm5d_team_stats(lfbm5d_team *T, unsigned long long *bytes_exchanged, unsigned *passes_redone, unsigned long long *tie_patches, int *peer_view)
 {
     if (!T) return;
     if (bytes_exchanged) *bytes_exchanged = T->bytes_exchanged;
     if (passes_redone) *passes_redone = T->passes_redone;
+    if (tie_patches) *tie_patches = T->tie_patches;
+    if (peer_view) *peer_view = T->peer_ready ? 1 : 0;
+}
+
+/* per-phase device time of the first local rank: out[0..7] = pad, est0 exchange, block matching, match exchange, selection + groups +
+ * aggregation 1, border exchange, aggregation 2, border + counter exchange; out[8..11] = inside block matching: self planes, partial
+ * selection, disparity planes, disparity argmin (ms since timing was switched on) */
+void lfbm5d_team_timing(lfbm5d_team *T, int on, float *out12)
+{
+    if (!T) return;
+    if (out12) for (int i = 0; i < 12; i++) out12[i] = T->phase_ms[i];
+    if (on && !T->tev[0]) { cudaSetDevice(T->local[0]->device); for (auto &e : T->tev) cudaEventCreate(&e); for (auto &e : T->bev) cudaEventCreate(&e); }
+    if (on != (T->timing ? 1 : 0)) for (auto &m : T->phase_ms) m = 0.f;
+    T->timing = on != 0;
+}
+
+/* tests: give up the peer view of the self sums, so that exact ties take the exchange-and-redo fallback */
+void lfbm5d_team_disable_peer_view(lfbm5d_team *T)
+{
+    if (!T) return;
+    if (T->comm) team_peer_close(T);
+    T->peer_ready = false; T->peer_ok = false;
 }
 
 } // extern "C"

@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(128) k_bm_partial(SelGeom g, const float *__re
 
 // Stage 2: the owner of reference patch r merges the partial lists of the G ranks ([G][R] counts, [G][R][NM] keys) and finishes
 // like k_bm_select_fast: nSx = min(N, 2^floor(log2 count)), indices in list order, duplicate when only one match; reference
-// patches with an exact float tie among the selected distances are listed (the team then redoes the pass's selection from the
-// complete sums, where the re-implemented libstdc++ partial_sort resolves them like the reference).
+// patches with an exact float tie among the selected distances are listed: k_bm_select then runs the re-implemented libstdc++
+// partial_sort on their complete candidate sequence, reading the sums of the other ranks' planes through peer pointers.
 template <int NM>
 __global__ void __launch_bounds__(128) k_bm_merge(SelGeom g, int G, int r0, int r1, const unsigned *__restrict__ cnt_all,
                                                   const unsigned long long *__restrict__ keys_all, unsigned *__restrict__ out_count,
-                                                  unsigned *__restrict__ out_idx, unsigned *__restrict__ tie_count)
+                                                  unsigned *__restrict__ out_idx, unsigned *__restrict__ tie_list, unsigned *__restrict__ tie_count)
 {
     const int r = r0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= r1) return;
@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(128) k_bm_merge(SelGeom g, int G, int r0, int 
 #pragma unroll
     for (int t = 0; t + 1 < NM; ++t)
         if (t + 1 < M && (unsigned) (top[t] >> 32) == (unsigned) (top[t + 1] >> 32)) tie = true;
-    if (tie) atomicAdd(tie_count, 1u);      // the values written below are then provisional
+    if (tie) {      // the values written below are then provisional: k_bm_select redoes the listed patches from the complete sums
+        const unsigned slot = atomicAdd(tie_count, 1u);
+        if (tie_list) tie_list[slot] = (unsigned) r;
+    }
     auto idx_of = [&](unsigned oo) -> unsigned {
         const int djx = (int) oo / Ns, rem = (int) oo - djx * Ns;
         const int di = rem <= nSim ? rem : -nSim + (rem - nSim - 1);

@@ -19,8 +19,10 @@ def run_single(L, eng, torch, noisy, mask, p1, p2):
     return w, b, o, s1
 
 
-def run_team(L, torch, world, noisy, mask, p1, p2, gather):
+def run_team(L, torch, world, noisy, mask, p1, p2, gather, peer_view=True):
     team = L.Team.emulated(0, world)
+    if not peer_view:
+        team.disable_peer_view()
     ws = [noisy.clone() for _ in range(world)]
     bs = [torch.zeros_like(noisy) for _ in range(world)]
     outs = [torch.zeros_like(noisy) for _ in range(world)]
@@ -66,9 +68,10 @@ def test_team_bit_identical_to_single(world, aw, ah, H, W, C, masked, oracle):
         assert torch.equal(outs[g][:, :, lo:keep], o0[:, :, lo:keep]), "denoised differs on rank %d" % g
 
 
-def test_team_ties_redo_the_selection(oracle):
-    """Quantised, partly flat light field: exact distance ties among the selected self matches make the team redo the pass's
-    selection from the complete sums (the re-implemented libstdc++ partial_sort), still bit-identical to one GPU."""
+def test_team_exact_distance_ties(oracle):
+    """Quantised, partly flat light field: reference patches with exact distance ties among their selected self matches need the
+    complete candidate sequence (the re-implemented libstdc++ partial_sort). With the peer view of the other ranks' sums they are
+    redone in place; without it the team exchanges the complete sums and redoes the pass. Bit-identical to one GPU either way."""
     import torch
     import lfbm5d_b200 as L
     dev = torch.device("cuda", 0)
@@ -83,7 +86,9 @@ def test_team_ties_redo_the_selection(oracle):
     eng = L.LFBM5D(0)
     w0, b0, o0, s0 = run_single(L, eng, torch, noisy, mask, p1, p2)
     eng.close()
-    ws, bs, outs, bands1, bands2, st = run_team(L, torch, 2, noisy, mask, p1, p2, gather=1)
-    assert st["passes_redone"] > 0
-    for g in range(2):
-        assert torch.equal(outs[g], o0) and torch.equal(ws[g], w0)
+    for peer_view in (True, False):
+        ws, bs, outs, bands1, bands2, st = run_team(L, torch, 3, noisy, mask, p1, p2, gather=1, peer_view=peer_view)
+        assert st["peer_view"] == peer_view
+        assert (st["tie_patches"] > 0 and st["passes_redone"] == 0) if peer_view else st["passes_redone"] > 0
+        for g in range(3):
+            assert torch.equal(outs[g], o0) and torch.equal(ws[g], w0)
