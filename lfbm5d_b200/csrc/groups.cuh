@@ -857,8 +857,10 @@ struct AggArgs {
 #define AGG_CAP_K8 1024     // list capacity for k = 8 (more, smaller patches per tile: one flush per tile) ...
 #define AGG_CAP_K16 768     // ... and otherwise (measured: 768 is faster for k = 16, 1024 for k = 8)
 
-// K, CC: compile-time patch size / channel count (0 = take them from the arguments)
-template <int K, int CC>
+// K, CC: compile-time patch size / channel count (0 = take them from the arguments); BAND: the launch covers the pixel rows
+// [y_lo, y_hi) and the reference rows a_min .. a_max only (team path) — kept out of the whole-plane variant, which sits exactly
+// at its register budget
+template <int K, int CC, bool BAND>
 __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
 {
     constexpr int AGG_CAP = K == 8 ? AGG_CAP_K8 : AGG_CAP_K16;
@@ -871,16 +873,16 @@ __global__ void __launch_bounds__(256, 4) k_aggregate(AggArgs g)
     if (!g.win.mask[st] || g.win.proc[st]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = K ? K : g.k, k2 = k * k, A = g.A, C = CC ? CC : g.C, N = g.N;
-    const int tyb = blockIdx.y + g.ty0;
+    const int tyb = BAND ? blockIdx.y + g.ty0 : blockIdx.y;
     const int y0 = tyb * 16, x0 = blockIdx.x * 16;
     // a warp owns an 8 (x) by 4 (y) block of the tile: the squarer the footprint, the fewer patches touch it and the more
     // of its lanes each of them covers
     const int wy0 = y0 + (warp >> 1) * 4, wx0 = x0 + (warp & 1) * 8;
     const int y = wy0 + (lane >> 3), x = wx0 + (lane & 7);
-    const bool inimg = y < g.y_hi && y >= g.y_lo && x < g.w;
+    const bool inimg = BAND ? (y < g.y_hi && y >= g.y_lo && x < g.w) : (y < g.h && x < g.w);
     const size_t plane = (size_t) g.w * g.h;
     for (int t = tid; t < k2; t += 256) skaiser[t] = c_tab.kaiser[t];
-    const int a_lo = max(g.arange[2 * tyb], g.a_min), a_hi = min(g.arange[2 * tyb + 1], g.a_max);
+    const int a_lo = BAND ? max(g.arange[2 * tyb], g.a_min) : g.arange[2 * tyb], a_hi = BAND ? min(g.arange[2 * tyb + 1], g.a_max) : g.arange[2 * tyb + 1];
     const int b_lo = g.brange[2 * blockIdx.x], b_hi = g.brange[2 * blockIdx.x + 1];
     const int nbn = (b_hi - b_lo + 1) * N;                 // candidates per reference row: (column, n)
     float num[3] = { 0.f, 0.f, 0.f }, den[3] = { 0.f, 0.f, 0.f };

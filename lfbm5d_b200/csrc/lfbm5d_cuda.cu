@@ -732,10 +732,11 @@ int launch_aggregate(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, in
     aa.y_lo = y_lo; aa.y_hi = y_hi; aa.a_min = a_lo; aa.a_max = a_hi - 1;
     aa.ty0 = y_lo / 16;
     dim3 grid((pc.wb + 15) / 16, (y_hi + 15) / 16 - aa.ty0, pc.A);
-    void (*kagg)(AggArgs) = k_aggregate<8, 1>;         // validate(): k is 8 or 16, C is 1 or 3
-    if (pc.C == 3 && pc.k == 16) kagg = k_aggregate<16, 3>;
-    else if (pc.C == 3 && pc.k == 8) kagg = k_aggregate<8, 3>;
-    else if (pc.C == 1 && pc.k == 16) kagg = k_aggregate<16, 1>;
+    const bool band = !(y_lo == 0 && y_hi == (int) pc.hb && a_lo == 0 && a_hi == pg.nr);
+    void (*kagg)(AggArgs) = band ? k_aggregate<8, 1, true> : k_aggregate<8, 1, false>;         // validate(): k is 8 or 16, C is 1 or 3
+    if (pc.C == 3 && pc.k == 16) kagg = band ? k_aggregate<16, 3, true> : k_aggregate<16, 3, false>;
+    else if (pc.C == 3 && pc.k == 8) kagg = band ? k_aggregate<8, 3, true> : k_aggregate<8, 3, false>;
+    else if (pc.C == 1 && pc.k == 16) kagg = band ? k_aggregate<16, 1, true> : k_aggregate<16, 1, false>;
     LAUNCH(ctx, kagg, grid, 256, 0, aa);
     return 0;
 }
