@@ -148,6 +148,9 @@ void lfbm5d_team_stats(lfbm5d_team *team, unsigned long long *bytes_exchanged, u
  * exchange, and inside block matching: self planes, partial selection, disparity planes, disparity argmin */
 void lfbm5d_team_timing(lfbm5d_team *team, int on, float *out12);
 void lfbm5d_team_disable_peer_view(lfbm5d_team *team);   /* tests: force the exchange-and-redo fallback */
+/* NCCL teams map each other's buffers with cudaIpc and exchange by storing straight into peer memory over NVLink (one copy kernel +
+ * flag per exchange); on = 0 keeps the mappings for the exact-tie path but sends the exchanges through NCCL send / recv (comparison) */
+void lfbm5d_team_use_peer_exchange(lfbm5d_team *team, int on);
 
 /* ---- parity/debug exports (used by tests only) ---------------------------------------------------
  * One window pass (the reference's bm5d_1st_step / bm5d_2nd_step, `pst == cst` branch) on HOST padded

@@ -36,6 +36,8 @@ enum TeamBuf { TB_EST0, TB_FIRST, TB_SHAPE, TB_PKEY_SEND, TB_PKEY_ALL, TB_PCNT_S
                TB_S_AT, TB_S_MIR, TB_GSEND, TB_GRECV, TB_NBUF };
 
 struct TeamSeg { int src, dst; int sbuf, dbuf; size_t soff, doff, bytes; };      // dst < 0: to every other rank, same place
+#define TSLOT 2048           // bytes per rank in the counter buffers (two halves, used alternately: a peer can be one exchange ahead)
+#define TSLOT_U64 256
 
 // ---- NCCL through dlopen: the library has no link-time dependency on it (single-GPU users never load it) ----
 struct NcclId { char internal[128]; };
@@ -85,11 +87,17 @@ struct lfbm5d_team {
     std::vector<float *> d_noisy, d_basic; // per local rank
     unsigned long long bytes_exchanged = 0;
     unsigned passes_redone = 0;
-    // peer view of the sampled self sums (exact-tie selection): per rank the device pointers of its s_at / s_mir as seen from
-    // here (emulated: the other contexts' buffers; NCCL: cudaIpc mappings over NVLink)
+    // peer view of the other ranks' buffers (emulated: the other contexts' buffers; NCCL teams: cudaIpc mappings, NVLink): the
+    // sampled self sums for the exact-tie selection, and every exchanged buffer for the direct peer-memory exchanges
     bool peer_ready = false, peer_ok = true;
     const float *peer_at[LF_MAXRANKS] = {}, *peer_mir[LF_MAXRANKS] = {};
-    bool peer_open[LF_MAXRANKS] = {};
+    char *peer_buf[LF_MAXRANKS][TB_NBUF] = {};
+    std::vector<void *> peer_opened;               // mappings to close
+    std::vector<std::vector<size_t>> peer_keys;    // geometries whose buffers have been allocated and mapped
+    unsigned xepoch = 0;                           // exchange counter (peer-memory exchanges)
+    unsigned cparity = 0;                          // which half of the counter buffers the next counter exchange uses
+    DevBuf xsegs, xflags, xdone, xflagptrs;
+    bool use_peer_exchange = true;
     unsigned long long tie_patches = 0;
     // per-phase device time of local rank 0 (lfbm5d_team_timing): events at the phase boundaries of a pass
     bool timing = false;
@@ -142,11 +150,50 @@ char *team_ptr(lfbm5d_ctx *ctx, int id)
     }
 }
 
+// Exchange over peer memory (NCCL teams whose buffers are mapped into each other with cudaIpc): ONE kernel stores this rank's
+// outgoing segments straight into the receivers' buffers over NVLink and then raises this exchange's number in every peer's flag
+// slot; a one-warp kernel waits for the peers' numbers. Every exchange is a barrier of the team, so a rank is at most one exchange
+// ahead of another: what exchange e + 1 writes never overlaps what a receiver still uses between e and e + 1 (team.cuh header:
+// disjoint rows / planes / slots per exchange; the counter buffers alternate between two halves).
+int team_exchange_peer(lfbm5d_team *T, const std::vector<TeamSeg> &segs)
+{
+    lfbm5d_ctx *ctx = T->local[0];
+    const int me = T->local_rank[0], G = T->world;
+    std::vector<PeerSegD> d;
+    unsigned long long chunks = 0;
+    for (const TeamSeg &s : segs) {
+        if (!s.bytes || s.src != me) continue;
+        for (int q = 0; q < G; q++) {
+            if (s.dst >= 0 ? q != s.dst : q == me) continue;
+            PeerSegD e;
+            e.src = team_ptr(ctx, s.sbuf) + s.soff;
+            e.dst = (q == me ? team_ptr(ctx, s.dbuf) : T->peer_buf[q][s.dbuf]) + s.doff;
+            e.bytes = s.bytes; e.first_chunk = chunks;
+            chunks += (s.bytes + PEER_CHUNK - 1) / PEER_CHUNK;
+            d.push_back(e);
+            if (q != me) T->bytes_exchanged += s.bytes;
+        }
+    }
+    if (!d.empty()) {
+        if (T->xsegs.ensure(d.size() * sizeof(PeerSegD))) return 1;
+        CK(cudaMemcpyAsync(T->xsegs.p, d.data(), d.size() * sizeof(PeerSegD), cudaMemcpyHostToDevice, ctx->stream));      // pageable: staged before the call returns
+    }
+    const unsigned epoch = ++T->xepoch;
+    const unsigned grid = (unsigned) std::max<unsigned long long>(1, std::min<unsigned long long>(chunks, (unsigned long long) ctx->num_sms * 8));
+    k_peer_copy<<<grid, 256, 0, ctx->stream>>>(T->xsegs.as<PeerSegD>(), (int) d.size(), (unsigned) chunks, T->xdone.as<unsigned>(),
+                                               T->xflagptrs.as<unsigned *>(), me, G, epoch);
+    k_peer_wait<<<1, 32, 0, ctx->stream>>>(T->xflags.as<unsigned>(), me, G, epoch);
+    ctx->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // Execute a list of segments. NCCL team: one group of sends / receives on the compute stream of the (single) local rank.
 // Emulated team: device copies between the contexts, fenced by device-wide synchronisations (test path).
 int team_exchange(lfbm5d_team *T, const std::vector<TeamSeg> &segs)
 {
     if (segs.empty()) return 0;
+    if (T->comm && T->peer_ready && T->use_peer_exchange) return team_exchange_peer(T, segs);
     if (T->comm) {
         lfbm5d_ctx *ctx = T->local[0];
         const int me = T->local_rank[0];
@@ -251,9 +298,12 @@ int team_ensure(lfbm5d_team *T, lfbm5d_ctx *ctx, const PassCfg &pc)
     const size_t NM = pc.N + 1, G = (size_t) T->world;
     if (pg.nself > 0 && (b->pkey_send.ensure((size_t) pg.R * NM * 8) || b->pkey_all.ensure(G * pg.R * NM * 8) || b->pcnt_send.ensure((size_t) pg.R * 4) ||
                          b->pcnt_all.ensure(G * pg.R * 4))) return 1;
-    if (b->counters.ensure(G * 64 * 8 + 64)) return 1;
+    if (b->counters.ensure(2 * G * TSLOT)) return 1;
     return 0;
 }
+
+// byte offset of rank g's slot in the half of the counter buffers the current counter exchange uses
+size_t cslot(const lfbm5d_team *T, int g) { return ((size_t) T->cparity * T->world + g) * TSLOT; }
 
 #define TMARK(i) do { if (T->timing) CK(cudaEventRecord(T->tev[i], T->local[0]->stream)); } while (0)
 
@@ -353,8 +403,8 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             const Band &bd = T->bands[g];
             TeamCtxBufs *b = team_bufs(ctx);
             CK(cudaSetDevice(ctx->device));
-            unsigned long long *cnts = b->counters.as<unsigned long long>() + (size_t) g * 64;
-            CK(cudaMemsetAsync(cnts, 0, 64 * 8, ctx->stream));
+            unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
+            CK(cudaMemsetAsync(cnts, 0, 64, ctx->stream));
             const int nown = bd.r1 - bd.r0;
             if (nown > 0) {
                 if (pg.nself > 0 && !redo) {
@@ -423,7 +473,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             TeamCtxBufs *b = team_bufs(ctx);
             CK(cudaSetDevice(ctx->device));
             if (bd.r1 > bd.r0 && launch_aggregate(ctx, pc, win, bd.y0, bd.pc1, bd.a0, bd.a1)) return 1;
-            unsigned long long *cnts = b->counters.as<unsigned long long>() + (size_t) g * 64;
+            unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
             if (bd.i1 > bd.i0)
                 LAUNCH(ctx, k_count_cov_rows, grid_for(ctx, (size_t) pc.A * C * (bd.i1 - bd.i0) * pc.W), 256, 0, ctx->densym.as<float>(), win, (int) pc.W, (int) pc.H,
                        C, (int) pc.n, (int) pc.k, bd.i0, bd.i1 - bd.i0, cnts);
@@ -443,7 +493,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                     }
                 }
             }
-            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, 24 });
+            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, cslot(T, g), cslot(T, g), 24 });
             if (team_exchange(T, segs)) return 1;
         }
         TMARK(8);
@@ -452,16 +502,17 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
         for (int l = 0; l < nl; l++) {
             lfbm5d_ctx *ctx = T->local[l];
             CK(cudaSetDevice(ctx->device));
-            std::vector<unsigned long long> h((size_t) G * 64);
-            CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            std::vector<unsigned long long> h((size_t) G * TSLOT_U64);
+            CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.as<char>() + cslot(T, 0), h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             if (l == 0)
                 for (int g = 0; g < G; g++) {
-                    total_cov += h[(size_t) g * 64]; total_ties += h[(size_t) g * 64 + 1] & 0xffffffffull;
-                    T->tie_patches += h[(size_t) g * 64 + 2] & 0xffffffffull;
+                    total_cov += h[(size_t) g * TSLOT_U64]; total_ties += h[(size_t) g * TSLOT_U64 + 1] & 0xffffffffull;
+                    T->tie_patches += h[(size_t) g * TSLOT_U64 + 2] & 0xffffffffull;
                 }
             ctx->stats.window_passes++;
         }
+        T->cparity ^= 1u;
         *cov = total_cov;
         if (T->timing) {    // phases 2..8: block matching, exchange, selection + groups + aggregation, exchange, aggregation 2, exchange
             for (int i = 2; i < 8; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
@@ -489,7 +540,7 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
             if (bd.c1 > bd.y0)
                 LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) pc.A * (bd.c1 - bd.y0) * wb), 256, 0, T->d_noisy[l], pc.step == 2 ? T->d_basic[l] : (const float *) nullptr,
                        ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
-                       ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.W, (int) pc.H, C, (int) pc.n, bd.y0, bd.c1 - bd.y0);
+                       ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.W, (int) pc.H, C, (int) pc.n, bd.y0, bd.c1 - bd.y0, bd.y1);
         }
         // est0 was overwritten on the own rows by k_pad_rows with the same values (num / den of the light field are unchanged)
     }
@@ -524,7 +575,7 @@ int team_count_zero(lfbm5d_team *T, const std::vector<int> &items, bool padded, 
         const int g = T->local_rank[l];
         const Band &bd = T->bands[g];
         CK(cudaSetDevice(ctx->device));
-        unsigned long long *cnts = team_bufs(ctx)->counters.as<unsigned long long>() + (size_t) g * 64;
+        unsigned long long *cnts = reinterpret_cast<unsigned long long *>(team_bufs(ctx)->counters.as<char>() + cslot(T, g));
         CK(cudaMemsetAsync(cnts, 0, 64 * 8, ctx->stream));
         for (int i = 0; i < nit; i++) {
             if (padded) {      // padded weights of window slot items[i], all channels, own rows [y0, y1)
@@ -537,17 +588,18 @@ int team_count_zero(lfbm5d_team *T, const std::vector<int> &items, bool padded, 
         }
     }
     std::vector<TeamSeg> segs;
-    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 64 * 8, (size_t) g * 64 * 8, (size_t) nit * 8 });
+    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, cslot(T, g), cslot(T, g), (size_t) nit * 8 });
     if (team_exchange(T, segs)) return 1;
     out.assign(nit, 0);
     for (int l = 0; l < nl; l++) {
         lfbm5d_ctx *ctx = T->local[l];
         CK(cudaSetDevice(ctx->device));
-        std::vector<unsigned long long> h((size_t) G * 64);
-        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<unsigned long long> h((size_t) G * TSLOT_U64);
+        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.as<char>() + cslot(T, 0), h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (l == 0) for (int g = 0; g < G; g++) for (int i = 0; i < nit; i++) out[i] += h[(size_t) g * 64 + i];
+        if (l == 0) for (int g = 0; g < G; g++) for (int i = 0; i < nit; i++) out[i] += h[(size_t) g * TSLOT_U64 + i];
     }
+    T->cparity ^= 1u;
     return 0;
 }
 
@@ -560,90 +612,113 @@ int team_host_allgather(lfbm5d_team *T, const void *mine_per_local, size_t bytes
         lfbm5d_ctx *ctx = T->local[l];
         CK(cudaSetDevice(ctx->device));
         TeamCtxBufs *b = team_bufs(ctx);
-        if (b->counters.ensure((size_t) G * 64 * 8 + 64)) return 1;
-        CK(cudaMemcpyAsync(b->counters.as<char>() + (size_t) T->local_rank[l] * 512, (const char *) mine_per_local + (size_t) l * bytes, bytes,
+        if (bytes > TSLOT) return fail("host all-gather: value too large");
+        if (b->counters.ensure((size_t) 2 * G * TSLOT)) return 1;
+        CK(cudaMemcpyAsync(b->counters.as<char>() + cslot(T, T->local_rank[l]), (const char *) mine_per_local + (size_t) l * bytes, bytes,
                            cudaMemcpyHostToDevice, ctx->stream));
     }
     std::vector<TeamSeg> segs;
-    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, (size_t) g * 512, (size_t) g * 512, bytes });
+    for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, cslot(T, g), cslot(T, g), bytes });
     if (team_exchange(T, segs)) return 1;
     all.assign((size_t) G * bytes, 0);
     for (int l = 0; l < nl; l++) {
         lfbm5d_ctx *ctx = T->local[l];
         CK(cudaSetDevice(ctx->device));
-        std::vector<unsigned char> h((size_t) G * 512);
-        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.p, h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<unsigned char> h((size_t) G * TSLOT);
+        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.as<char>() + cslot(T, 0), h.size(), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (l == 0) for (int g = 0; g < G; g++) memcpy(all.data() + (size_t) g * bytes, h.data() + (size_t) g * 512, bytes);
+        if (l == 0) for (int g = 0; g < G; g++) memcpy(all.data() + (size_t) g * bytes, h.data() + (size_t) g * TSLOT, bytes);
     }
+    T->cparity ^= 1u;
     return 0;
 }
 
 void team_peer_close(lfbm5d_team *T)
 {
-    for (int g = 0; g < LF_MAXRANKS; g++)
-        if (T->peer_open[g]) {
-            cudaIpcCloseMemHandle(const_cast<float *>(T->peer_at[g]));
-            cudaIpcCloseMemHandle(const_cast<float *>(T->peer_mir[g]));
-            T->peer_open[g] = false;
-        }
+    for (void *p : T->peer_opened) cudaIpcCloseMemHandle(p);
+    T->peer_opened.clear();
     T->peer_ready = false;
 }
 
-// Make the self sums of every rank addressable from every rank. s_at / s_mir are (re)allocated here, with all peer mappings closed
-// first (an exported allocation must not be freed while it is mapped elsewhere), then exported / imported again.
-int team_peer_setup(lfbm5d_team *T, const PassCfg &pc)
+// Allocate every buffer a step with geometry pc needs and make the exchanged ones addressable from every rank. DevBufs only grow,
+// and every rank sees the same sequence of geometries: a geometry that was set up before needs nothing. For a new one all peer
+// mappings are closed first (an exported allocation must not be freed while it is mapped elsewhere), the buffers are (re)allocated,
+// and everything is exported / imported again.
+int team_peer_setup(lfbm5d_team *T, const PassCfg &pc, int step)
 {
     const PassGeom pg = pass_geom(pc);
     const int G = T->world, nl = (int) T->local.size();
-    const size_t need = (size_t) pg.nself * pg.R * 4;
-    if (need == 0) return 0;
+    auto ensure_all = [&](lfbm5d_ctx *ctx) -> int {
+        CK(cudaSetDevice(ctx->device));
+        if (ensure_pass_buffers(ctx, pc) || team_ensure(T, ctx, pc)) return 1;
+        // gather buffers of team_step_end
+        size_t maxrows = 0;
+        for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (T->bands[g].i1 - T->bands[g].i0));
+        const size_t blk = (size_t) T->ss.asize() * pc.C * maxrows * pc.W * 4;
+        TeamCtxBufs *b = team_bufs(ctx);
+        if (b->gsend.ensure(blk) || b->grecv.ensure(blk * G)) return 1;
+        return 0;
+    };
     if (!T->comm) {      // emulated: all contexts live here
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            CK(cudaSetDevice(ctx->device));
-            if (ctx->s_at.ensure(need) || ctx->s_mir.ensure(need)) return 1;
-        }
+        for (int l = 0; l < nl; l++) if (ensure_all(T->local[l])) return 1;
         for (int l = 0; l < nl; l++) { T->peer_at[T->local_rank[l]] = T->local[l]->s_at.as<float>(); T->peer_mir[T->local_rank[l]] = T->local[l]->s_mir.as<float>(); }
         T->peer_ready = T->peer_ok;
         return 0;
     }
     lfbm5d_ctx *ctx = T->local[0];
     const int me = T->local_rank[0];
-    CK(cudaSetDevice(ctx->device));
-    unsigned long long flag = (need > ctx->s_at.cap || need > ctx->s_mir.cap || !T->peer_ready) ? 1 : 0;
-    std::vector<unsigned char> all;
-    if (team_host_allgather(T, &flag, 8, all)) return 1;
-    bool any = false;
-    for (int g = 0; g < G; g++) any = any || *reinterpret_cast<unsigned long long *>(all.data() + (size_t) g * 8) != 0;
-    if (!any) return 0;
+    const std::vector<size_t> key = { (size_t) step, (size_t) pc.wb, (size_t) pc.hb, (size_t) pc.k, (size_t) pc.N, (size_t) pc.A, (size_t) pc.C, (size_t) pc.nSim,
+                                      (size_t) pc.nDisp, (size_t) pg.R, (size_t) T->ss.asize() };
+    for (auto &k : T->peer_keys) if (k == key) return ensure_all(ctx);      // nothing grows: no reallocation, mappings stay valid
+    T->peer_keys.push_back(key);
     team_peer_close(T);
-    if (team_host_allgather(T, &flag, 8, all)) return 1;        // barrier: every mapping is closed before anybody frees
-    const size_t want = need + need / 8;                          // some room: the next step's grid may be a little larger
-    if (need > ctx->s_at.cap && ctx->s_at.ensure(want)) return 1;
-    if (need > ctx->s_mir.cap && ctx->s_mir.ensure(want)) return 1;
-    struct { cudaIpcMemHandle_t at, mir; unsigned long long ok; } mine;
+    std::vector<unsigned char> all;
+    unsigned long long z = 0;
+    if (team_host_allgather(T, &z, 8, all)) return 1;        // barrier (over NCCL: the mappings are gone): everything is closed before anybody frees
+    if (ensure_all(ctx)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    if (T->xflags.ensure(LF_MAXRANKS * 4 * 2) == 0 && T->xflags.cap && T->xepoch == 0) CK(cudaMemsetAsync(T->xflags.p, 0, T->xflags.cap, ctx->stream));
+    if (T->xdone.ensure(64)) return 1;
+    CK(cudaMemsetAsync(T->xdone.p, 0, 64, ctx->stream));
+    if (T->xflagptrs.ensure(LF_MAXRANKS * sizeof(void *))) return 1;
+    if (!T->peer_ok) return 0;
+    // export: TB_NBUF buffers + the flag slots
+    struct Exp { cudaIpcMemHandle_t h[TB_NBUF + 1]; unsigned char have[TB_NBUF + 1]; unsigned char ok; };
+    static_assert(sizeof(Exp) <= TSLOT, "handles do not fit the counter slot");
+    Exp mine;
     memset(&mine, 0, sizeof(mine));
-    mine.ok = T->peer_ok && cudaIpcGetMemHandle(&mine.at, ctx->s_at.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.mir, ctx->s_mir.p) == cudaSuccess;
-    cudaGetLastError();
+    mine.ok = 1;
+    for (int b = 0; b <= TB_NBUF; b++) {
+        void *p = b < TB_NBUF ? (void *) team_ptr(ctx, b) : T->xflags.p;
+        if (!p) continue;
+        if (cudaIpcGetMemHandle(&mine.h[b], p) == cudaSuccess) mine.have[b] = 1; else { mine.ok = 0; cudaGetLastError(); }
+    }
     if (team_host_allgather(T, &mine, sizeof(mine), all)) return 1;
     bool ok = true;
-    for (int g = 0; g < G; g++) ok = ok && reinterpret_cast<decltype(mine) *>(all.data() + (size_t) g * sizeof(mine))->ok != 0;
+    for (int g = 0; g < G; g++) ok = ok && reinterpret_cast<Exp *>(all.data() + (size_t) g * sizeof(Exp))->ok != 0;
+    std::vector<unsigned *> flagptrs(LF_MAXRANKS, nullptr);
     if (ok)
         for (int g = 0; g < G && ok; g++) {
-            if (g == me) { T->peer_at[g] = ctx->s_at.as<float>(); T->peer_mir[g] = ctx->s_mir.as<float>(); continue; }
-            auto *h = reinterpret_cast<decltype(mine) *>(all.data() + (size_t) g * sizeof(mine));
-            void *pa = nullptr, *pm = nullptr;
-            if (cudaIpcOpenMemHandle(&pa, h->at, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-                cudaIpcOpenMemHandle(&pm, h->mir, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); if (pa) cudaIpcCloseMemHandle(pa); break; }
-            T->peer_at[g] = (const float *) pa; T->peer_mir[g] = (const float *) pm; T->peer_open[g] = true;
+            const Exp *e = reinterpret_cast<Exp *>(all.data() + (size_t) g * sizeof(Exp));
+            for (int b = 0; b <= TB_NBUF && ok; b++) {
+                void *p = nullptr;
+                if (g == me) p = b < TB_NBUF ? (void *) team_ptr(ctx, b) : T->xflags.p;
+                else if (e->have[b]) {
+                    if (cudaIpcOpenMemHandle(&p, e->h[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+                    T->peer_opened.push_back(p);
+                }
+                if (b < TB_NBUF) T->peer_buf[g][b] = (char *) p; else flagptrs[g] = (unsigned *) p;
+            }
+            T->peer_at[g] = (const float *) T->peer_buf[g][TB_S_AT]; T->peer_mir[g] = (const float *) T->peer_buf[g][TB_S_MIR];
         }
-    // everybody must agree (a rank that could not map its peers makes the whole team take the exchange-based fallback)
+    // everybody must agree (a rank that could not map its peers makes the whole team fall back to NCCL exchanges)
     unsigned long long okf = ok ? 1 : 0;
     if (team_host_allgather(T, &okf, 8, all)) return 1;
     for (int g = 0; g < G; g++) ok = ok && *reinterpret_cast<unsigned long long *>(all.data() + (size_t) g * 8) != 0;
-    if (!ok) { team_peer_close(T); T->peer_ok = false; }
-    T->peer_ready = ok;
+    if (!ok) { team_peer_close(T); T->peer_ok = false; return 0; }
+    CK(cudaMemcpyAsync(T->xflagptrs.p, flagptrs.data(), LF_MAXRANKS * sizeof(void *), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    T->peer_ready = true;
     return 0;
 }
 
@@ -691,11 +766,11 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
         CK(cudaMemsetAsync(ctx->num.p, 0, asize * each * 4, ctx->stream));
         CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
     }
-    if (team_peer_setup(T, S.pc)) return 1;       // (re)allocates s_at / s_mir under the export protocol, before ensure_pass_buffers sees them
+    if (team_peer_setup(T, S.pc, step)) return 1;       // allocates the pass buffers (under the export protocol of NCCL teams)
     for (int l = 0; l < nl; l++) {
         lfbm5d_ctx *ctx = T->local[l];
         CK(cudaSetDevice(ctx->device));
-        if (setup_tables(ctx, step, p, S.tau_4D) || ensure_pass_buffers(ctx, S.pc) || upload_grid(ctx, S.pc) || team_ensure(T, ctx, S.pc)) return 1;
+        if (setup_tables(ctx, step, p, S.tau_4D) || upload_grid(ctx, S.pc)) return 1;
     }
     return 0;
 }
@@ -769,7 +844,7 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
         if (bd.c1 > bd.y0)
             LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) Aw * (bd.c1 - bd.y0) * pc.wb), 256, 0, T->d_noisy[l], step == 2 ? T->d_basic[l] : (const float *) nullptr,
                    ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
-                   ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, bd.y0, bd.c1 - bd.y0);
+                   ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, bd.y0, bd.c1 - bd.y0, bd.y1);
     }
     const unsigned max_unproc = n_unproc;
     unsigned calls = 0;
@@ -950,12 +1025,14 @@ void lfbm5d_team_destroy(lfbm5d_team *T)
 {
     if (!T) return;
     for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
-    if (T->comm && T->peer_ready) {      // nobody frees its sums while they are mapped elsewhere
+    if (T->comm && T->peer_ready) {      // nobody frees its buffers while they are mapped elsewhere
         team_peer_close(T);
         unsigned long long z = 0;
         std::vector<unsigned char> all;
         team_host_allgather(T, &z, 8, all);
+        for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     }
+    T->xsegs.release(); T->xflags.release(); T->xdone.release(); T->xflagptrs.release();
     for (auto c : T->local) team_bufs_release(c);
     if (T->comm) g_nccl.CommDestroy(T->comm);
     if (T->owns_ctx) for (auto c : T->local) lfbm5d_destroy(c);
@@ -1064,5 +1141,8 @@ void lfbm5d_team_disable_peer_view(lfbm5d_team *T)
     if (T->comm) team_peer_close(T);
     T->peer_ready = false; T->peer_ok = false;
 }
+
+/* 0: exchanges of an NCCL team go through NCCL send / recv even when the buffers are peer-mapped (comparison runs) */
+void lfbm5d_team_use_peer_exchange(lfbm5d_team *T, int on) { if (T) T->use_peer_exchange = on != 0; }
 
 } // extern "C"

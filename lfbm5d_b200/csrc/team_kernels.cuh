@@ -12,8 +12,9 @@
 __global__ void k_pad_rows(const float *__restrict__ noisy, const float *__restrict__ basic, const float *__restrict__ num,
                            const float *__restrict__ den, float *__restrict__ nsym, float *__restrict__ bsym,
                            float *__restrict__ numsym, float *__restrict__ densym, float *__restrict__ est0,
-                           LfWindow win, int W, int H, int C, int n, int y_lo, int nrows)
+                           LfWindow win, int W, int H, int C, int n, int y_lo, int nrows, int est_hi)
 {
+    // est0 is written below row est_hi only: the running estimate of the rows shared with the next rank comes from their owner
     const int wb = W + 2 * n, hb = H + 2 * n;
     const size_t plane_b = (size_t) wb * hb, plane = (size_t) W * H, band = (size_t) nrows * wb;
     const size_t total = (size_t) win.A * band;
@@ -33,7 +34,7 @@ __global__ void k_pad_rows(const float *__restrict__ noisy, const float *__restr
             densym[dst + c * plane_b] = dv;
             float bv = 0.f;
             if (basic) { bv = basic[src + c * plane]; bsym[dst + c * plane_b] = bv; }
-            if (c == 0) est0[(size_t) a * plane_b + r] = dv ? uv / dv : (basic ? bv : nv);
+            if (c == 0 && i < est_hi) est0[(size_t) a * plane_b + r] = dv ? uv / dv : (basic ? bv : nv);
         }
     }
 }
@@ -273,4 +274,66 @@ __global__ void k_bm_identity_rows(const int *rows, const int *cols, int nc, int
     if (r >= r1) return;
     out_count[r] = 1;
     out_idx[(size_t) r * (N + 1)] = (unsigned) (rows[r / nc] * w + cols[r % nc]);    // core:3448-3460
+}
+
+// ---- exchanges over peer memory (NVLink stores into the other ranks' buffers, mapped with cudaIpc) ----
+// One kernel per exchange copies this rank's outgoing segments straight into their place in the receivers' buffers; the last CTA
+// to finish then writes the exchange number into every peer's flag slot (after a system-scope fence: a peer that sees the number
+// also sees the data). k_peer_wait is the other half: it returns once every peer's number has arrived.
+struct PeerSegD { const char *src; char *dst; unsigned long long bytes; unsigned long long first_chunk; };
+#define PEER_CHUNK 16384u
+
+__global__ void __launch_bounds__(256) k_peer_copy(const PeerSegD *__restrict__ segs, int nseg, unsigned nchunks, unsigned *done_counter,
+                                                   unsigned *const *peer_flags, int me, int G, unsigned epoch)
+{
+    __shared__ int s_seg;
+    for (unsigned ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        if (threadIdx.x == 0) {      // which segment this chunk belongs to (few segments: linear scan)
+            int q = 0;
+            while (q + 1 < nseg && segs[q + 1].first_chunk <= ch) ++q;
+            s_seg = q;
+        }
+        __syncthreads();
+        const PeerSegD sg = segs[s_seg];
+        const unsigned long long off = (unsigned long long) (ch - sg.first_chunk) * PEER_CHUNK;
+        const unsigned n = (unsigned) min((unsigned long long) PEER_CHUNK, sg.bytes - off);
+        const char *s = sg.src + off;
+        char *d = sg.dst + off;
+        if ((((size_t) s | (size_t) d) & 15) == 0) {
+            const unsigned nv = n >> 4;
+            for (unsigned i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<uint4 *>(d)[i] = reinterpret_cast<const uint4 *>(s)[i];
+            for (unsigned i = (nv << 4) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else if ((((size_t) s | (size_t) d) & 3) == 0) {
+            const unsigned nv = n >> 2;
+            for (unsigned i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<unsigned *>(d)[i] = reinterpret_cast<const unsigned *>(s)[i];
+            for (unsigned i = (nv << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        } else
+            for (unsigned i = threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+        __syncthreads();
+    }
+    // last CTA out: publish
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) *done_counter = 0u;
+        __threadfence_system();
+        if ((int) threadIdx.x < G && (int) threadIdx.x != me)
+            asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(peer_flags[threadIdx.x] + me), "r"(epoch) : "memory");
+    }
+}
+
+__global__ void k_peer_wait(const unsigned *flags, int me, int G, unsigned epoch)
+{
+    const int q = threadIdx.x;
+    if (q < G && q != me) {
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flags + q) : "memory");
+            if ((int) (v - epoch) >= 0) break;
+            __nanosleep(100);
+        }
+    }
 }
