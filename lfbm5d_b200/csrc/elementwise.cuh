@@ -182,8 +182,9 @@ __global__ void k_count_zero(const float *__restrict__ den, size_t nelem, unsign
 // 1414-1419): out = den ? num/den : sub, then out, noisy (and basic) go back to RGB. C == 3 path handles colour;
 // for C == 1 or RGB colour_space `docolor` is 0.
 __global__ void k_final(const float *__restrict__ num, const float *__restrict__ den, float *noisy, float *basic, float *out,
-                        const unsigned *mask, unsigned nsai, size_t HW, int C, int step, unsigned cs, int docolor)
+                        const unsigned *mask, unsigned nsai, size_t HW, int C, int step, unsigned cs, int docolor, int inputs_back = 1)
 {
+    // inputs_back = 0: noisy / basic stay in the working colour space (host entry points: their round-tripped copies went back early)
     const size_t total = (size_t) nsai * HW;
     for (size_t t = (size_t) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t) gridDim.x * blockDim.x) {
         const unsigned st = (unsigned) (t / HW);
@@ -199,12 +200,14 @@ __global__ void k_final(const float *__restrict__ num, const float *__restrict__
         if (docolor) {
             float a, b, c2;
             lf_color_px(cs, false, e[0], e[1], e[2], a, b, c2); e[0] = a; e[1] = b; e[2] = c2;
-            lf_color_px(cs, false, nz[0], nz[1], nz[2], a, b, c2); nz[0] = a; nz[1] = b; nz[2] = c2;
-            if (step == 2) { lf_color_px(cs, false, bs[0], bs[1], bs[2], a, b, c2); bs[0] = a; bs[1] = b; bs[2] = c2; }
+            if (inputs_back) {
+                lf_color_px(cs, false, nz[0], nz[1], nz[2], a, b, c2); nz[0] = a; nz[1] = b; nz[2] = c2;
+                if (step == 2) { lf_color_px(cs, false, bs[0], bs[1], bs[2], a, b, c2); bs[0] = a; bs[1] = b; bs[2] = c2; }
+            }
         }
         for (int c = 0; c < C; c++) {
             out[base + c * HW] = e[c];
-            if (docolor) {
+            if (docolor && inputs_back) {
                 noisy[base + c * HW] = nz[c];
                 if (step == 2) basic[base + c * HW] = bs[c];
             }

@@ -150,8 +150,26 @@ struct StepState {
     }
 };
 
+// Host entry points (lfbm5d_step1 / lfbm5d_step2): the light field travels SAI by SAI. Uploads (and the colour transform of each SAI)
+// run on their own stream in the order the static window plan needs the SAIs, every window waits for the events of its SAIs only;
+// an SAI is finalised (num / den, inverse colour transform) and sent back as soon as the last window of the plan that contains it
+// is done. PCIe traffic so runs under the window passes in both directions.
+struct HostIO {
+    bool on = false;
+    float *const *h_out = nullptr;
+    float *d_out = nullptr;
+    std::vector<cudaEvent_t> up, fin;      // per SAI: inputs on the device / final estimate computed
+    std::vector<int> last_use;             // last plan window containing the SAI
+    std::vector<unsigned> plan;            // (ps, pt) per plan window
+    std::vector<char> done;
+    bool plan_ok = true;
+    unsigned window = 0;
+};
+
 struct lfbm5d_ctx {
     StepState ss;
+    HostIO io;
+    cudaStream_t stream4 = nullptr;                       // device -> host copies of finished SAIs
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: early device->host copies of the host entry points
     cudaStream_t stream3 = nullptr;                       // disparity matching of a pass, beside the self matching on `stream`
@@ -879,7 +897,7 @@ int step_begin(lfbm5d_ctx *ctx, int step_, const lfbm5d_params *p_, float *d_noi
     CK(cudaMemcpyAsync(ctx->mask.p, mask.data(), asize * 4, cudaMemcpyHostToDevice, ctx->stream));
     const bool docolor = C == 3 && p->color_space != LFBM5D_RGB;
     S0.docolor = docolor;
-    if (docolor) {
+    if (docolor && !ctx->io.on) {      // (host entry points: done SAI by SAI behind the uploads)
         LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_noisy, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
         if (step == 2) LAUNCH(ctx, k_color, grid_for(ctx, asize * HW), 256, 0, d_basic, ctx->mask.as<unsigned>(), asize, HW, p->color_space, 1);
     }
@@ -976,6 +994,8 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, int force_sadct = -1)
         if (setup_tables(ctx, step, p, tau_4D)) return 1;
         S.tables_tau4 = tau_4D;
     }
+    if (ctx->io.on)
+        for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) CK(cudaStreamWaitEvent(ctx->stream, ctx->io.up[win.st[a]], 0));
     LAUNCH(ctx, k_pad_window, grid_for(ctx, (size_t) Aw * pc.wb * pc.hb), 256, 0, d_noisy, step == 2 ? d_basic : (const float *) nullptr,
            ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
            ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n);
@@ -1039,6 +1059,36 @@ int step_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, int force_sadct = -1)
     return 0;
 }
 
+// final estimate of one SAI (bm5d.cpp:405 / :706 + inverse colour transform) and its way back to the host
+int io_finish_sai(lfbm5d_ctx *ctx, unsigned st)
+{
+    StepState &S = ctx->ss;
+    const lfbm5d_params *p = &S.p;
+    const size_t HW = (size_t) p->width * p->height, each = HW * p->chnls;
+    HostIO &io = ctx->io;
+    LAUNCH(ctx, k_final, grid_for(ctx, HW), 256, 0, ctx->num.as<float>() + st * each, ctx->den.as<float>() + st * each, S.d_noisy + st * each,
+           S.d_basic ? S.d_basic + st * each : (float *) nullptr, io.d_out + st * each, ctx->mask.as<unsigned>() + st, 1u, HW, (int) p->chnls, S.step,
+           p->color_space, S.docolor ? 1 : 0, 0);
+    CK(cudaEventRecord(io.fin[st], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream4, io.fin[st], 0));
+    CK(cudaMemcpyAsync(io.h_out[st], io.d_out + st * each, each * 4, cudaMemcpyDeviceToHost, ctx->stream4));
+    io.done[st] = 1;
+    return 0;
+}
+
+// after window number io.window of the step: SAIs no later plan window touches are final
+int io_after_window(lfbm5d_ctx *ctx, unsigned ps, unsigned pt, unsigned calls)
+{
+    HostIO &io = ctx->io;
+    const unsigned i = io.window++;
+    if (!io.plan_ok) return 0;
+    if (2 * i + 1 >= io.plan.size() || io.plan[2 * i] != ps || io.plan[2 * i + 1] != pt || calls != 1) { io.plan_ok = false; return 0; }      // the run left the static plan
+    const unsigned asize = ctx->ss.asize();
+    for (unsigned st = 0; st < asize; st++)
+        if (ctx->ss.mask[st] && !io.done[st] && io.last_use[st] == (int) i && io_finish_sai(ctx, st)) return 1;
+    return 0;
+}
+
 int step_end(lfbm5d_ctx *ctx, float *d_out)
 {
     StepState &S = ctx->ss;
@@ -1048,8 +1098,11 @@ int step_end(lfbm5d_ctx *ctx, float *d_out)
     const unsigned asize = S.asize(), C = p->chnls;
     const size_t HW = (size_t) p->width * p->height;
     const bool docolor = S.docolor;
-    LAUNCH(ctx, k_final, grid_for(ctx, asize * HW), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), d_noisy, d_basic, d_out,
-           ctx->mask.as<unsigned>(), asize, HW, (int) C, step, p->color_space, docolor ? 1 : 0);
+    if (ctx->io.on) {      // whatever the plan did not finish early
+        for (unsigned st = 0; st < asize; st++) if (S.mask[st] && !ctx->io.done[st] && io_finish_sai(ctx, st)) return 1;
+    } else
+        LAUNCH(ctx, k_final, grid_for(ctx, asize * HW), 256, 0, ctx->num.as<float>(), ctx->den.as<float>(), d_noisy, d_basic, d_out,
+               ctx->mask.as<unsigned>(), asize, HW, (int) C, step, p->color_space, docolor ? 1 : 0);
     CK(cudaGetLastError());
     if (ctx->timing) {
         cudaEvent_t e_end = nullptr;
@@ -1073,6 +1126,7 @@ int step_device(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *d_nois
     while (ctx->ss.remaining) {
         unsigned ps = 0, pt = 0;
         if (step_select(ctx, ps, pt) || step_window(ctx, ps, pt)) return 1;
+        if (ctx->io.on && io_after_window(ctx, ps, pt, ctx->sched.back())) return 1;
         if (ctx->max_passes && ctx->ss.passes >= ctx->max_passes) break;
     }
     return step_end(ctx, d_out);
@@ -1223,6 +1277,7 @@ int lfbm5d_create(lfbm5d_ctx **out, int device)
     CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_rt, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->stream4, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaEventCreate(&ctx->ev_satb));
@@ -1247,6 +1302,9 @@ void lfbm5d_destroy(lfbm5d_ctx *ctx)
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_rt) cudaEventDestroy(ctx->ev_rt);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->stream4) cudaStreamDestroy(ctx->stream4);
+    for (auto e : ctx->io.up) cudaEventDestroy(e);
+    for (auto e : ctx->io.fin) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_satb) cudaEventDestroy(ctx->ev_satb);
@@ -1271,37 +1329,86 @@ int lfbm5d_step2_device(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *d_noisy_
     return step_device(ctx, 2, p, d_noisy_io, d_basic_io, d_denoised_out, sai_mask);
 }
 
+// One step through the host entry points, pipelined SAI by SAI (HostIO): uploads + colour transform on stream2 in the order of the
+// static plan, early return of the colour-round-tripped inputs and of the finished SAIs on stream4, the passes on the main stream.
+static int step_host(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *const *noisy_io, float *const *basic_io, const unsigned *sai_mask,
+                     float *const *out_host)
+{
+    if (validate(p, step)) return 1;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned asize = p->awidth * p->aheight;
+    const size_t HW = (size_t) p->width * p->height, each = HW * p->chnls;
+    if (ctx->noisy.ensure(asize * each * 4) || ctx->out.ensure(asize * each * 4) || ctx->mask.ensure(asize * 4)) return 1;
+    if (step == 2 && ctx->basic.ensure(asize * each * 4)) return 1;
+    const bool docolor = p->chnls == 3 && p->color_space != LFBM5D_RGB;
+    if (docolor && (ctx->rt_noisy.ensure(asize * each * 4) || (step == 2 && ctx->rt_basic.ensure(asize * each * 4)))) return 1;
+    HostIO &io = ctx->io;
+    while (io.up.size() < asize) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); io.up.push_back(e); }
+    while (io.fin.size() < asize) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); io.fin.push_back(e); }
+    // static plan of the step: upload order = order of first use; last_use = when an SAI becomes final
+    std::vector<unsigned> plan6((size_t) (asize + 1) * 6);
+    const unsigned nwin = lfbm5d_step_plan(p, sai_mask, plan6.data(), asize + 1);
+    const unsigned asw = 2 * p->an + 1;
+    io.plan.clear(); io.last_use.assign(asize, -1); io.done.assign(asize, 0); io.plan_ok = true; io.window = 0;
+    io.h_out = out_host; io.d_out = ctx->out.as<float>();
+    std::vector<unsigned> order;
+    std::vector<char> queued(asize, 0);
+    for (unsigned i = 0; i < nwin; i++) {
+        const unsigned *e = &plan6[6 * i];
+        io.plan.push_back(e[0]); io.plan.push_back(e[1]);
+        for (unsigned s = e[2]; s < e[2] + asw; s++)
+            for (unsigned t = e[3]; t < e[3] + asw; t++) {
+                const unsigned st = p->ang_major == LFBM5D_ROWMAJOR ? s * p->awidth + t : s + t * p->aheight;
+                io.last_use[st] = (int) i;
+                if (sai_mask[st] && !queued[st]) { queued[st] = 1; order.push_back(st); }
+            }
+    }
+    for (unsigned st = 0; st < asize; st++) if (sai_mask[st] && !queued[st]) order.push_back(st);
+    cudaStream_t sU = ctx->stream2, sD = ctx->stream4;
+    // the buffers may still be read by copies of an earlier call on these streams: they were synchronised at its end
+    CK(cudaMemcpyAsync(ctx->mask.p, sai_mask, asize * 4, cudaMemcpyHostToDevice, sU));
+    for (unsigned st : order) {
+        float *dn = ctx->noisy.as<float>() + st * each, *db = step == 2 ? ctx->basic.as<float>() + st * each : nullptr;
+        CK(cudaMemcpyAsync(dn, noisy_io[st], each * 4, cudaMemcpyHostToDevice, sU));
+        if (db) CK(cudaMemcpyAsync(db, basic_io[st], each * 4, cudaMemcpyHostToDevice, sU));
+        if (docolor) {
+            const unsigned *m1 = ctx->mask.as<unsigned>() + st;
+            // what the reference leaves in its inputs (forward then inverse transform), then the working colour space in place
+            LAUNCH_ON(ctx, sU, k_roundtrip, grid_for(ctx, HW), 256, 0, dn, ctx->rt_noisy.as<float>() + st * each, m1, 1u, HW, p->color_space);
+            LAUNCH_ON(ctx, sU, k_color, grid_for(ctx, HW), 256, 0, dn, m1, 1u, HW, p->color_space, 1);
+            if (db) {
+                LAUNCH_ON(ctx, sU, k_roundtrip, grid_for(ctx, HW), 256, 0, db, ctx->rt_basic.as<float>() + st * each, m1, 1u, HW, p->color_space);
+                LAUNCH_ON(ctx, sU, k_color, grid_for(ctx, HW), 256, 0, db, m1, 1u, HW, p->color_space, 1);
+            }
+        }
+        CK(cudaEventRecord(io.up[st], sU));
+        if (docolor) {
+            CK(cudaStreamWaitEvent(sD, io.up[st], 0));
+            CK(cudaMemcpyAsync(noisy_io[st], ctx->rt_noisy.as<float>() + st * each, each * 4, cudaMemcpyDeviceToHost, sD));
+            if (db) CK(cudaMemcpyAsync(basic_io[st], ctx->rt_basic.as<float>() + st * each, each * 4, cudaMemcpyDeviceToHost, sD));
+        }
+    }
+    io.on = true;
+    const int rc = step_device(ctx, step, p, ctx->noisy.as<float>(), step == 2 ? ctx->basic.as<float>() : nullptr, ctx->out.as<float>(), sai_mask);
+    io.on = false;
+    cudaStreamSynchronize(sU);
+    cudaStreamSynchronize(sD);
+    if (rc) return 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int lfbm5d_step1(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out)
 {
     if (!ctx || !noisy_io || !sai_mask || !basic_out) return fail("null argument");
-    if (validate(p, 1)) return 1;
-    CK(cudaSetDevice(ctx->device));
-    const unsigned asize = p->awidth * p->aheight;
-    const size_t each = (size_t) p->width * p->height * p->chnls;
-    if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || ctx->out.ensure(asize * each * 4)) return 1;
-    if (early_roundtrip(ctx, p, ctx->noisy, ctx->rt_noisy, noisy_io, sai_mask, asize, each)) return 1;
-    if (step_device(ctx, 1, p, ctx->noisy.as<float>(), nullptr, ctx->out.as<float>(), sai_mask)) { cudaStreamSynchronize(ctx->stream2); return 1; }
-    if (download_lf(ctx, ctx->out, basic_out, sai_mask, asize, each)) return 1;
-    CK(cudaStreamSynchronize(ctx->stream2));
-    return 0;
+    return step_host(ctx, 1, p, noisy_io, nullptr, sai_mask, basic_out);
 }
 
 int lfbm5d_step2(lfbm5d_ctx *ctx, const lfbm5d_params *p, float *const *noisy_io, float *const *basic_io, const unsigned *sai_mask,
                  float *const *denoised_out)
 {
     if (!ctx || !noisy_io || !basic_io || !sai_mask || !denoised_out) return fail("null argument");
-    if (validate(p, 2)) return 1;
-    CK(cudaSetDevice(ctx->device));
-    const unsigned asize = p->awidth * p->aheight;
-    const size_t each = (size_t) p->width * p->height * p->chnls;
-    if (upload_lf(ctx, ctx->noisy, noisy_io, sai_mask, asize, each) || upload_lf(ctx, ctx->basic, basic_io, sai_mask, asize, each) ||
-        ctx->out.ensure(asize * each * 4)) return 1;
-    if (early_roundtrip(ctx, p, ctx->noisy, ctx->rt_noisy, noisy_io, sai_mask, asize, each) ||
-        early_roundtrip(ctx, p, ctx->basic, ctx->rt_basic, basic_io, sai_mask, asize, each)) return 1;
-    if (step_device(ctx, 2, p, ctx->noisy.as<float>(), ctx->basic.as<float>(), ctx->out.as<float>(), sai_mask)) { cudaStreamSynchronize(ctx->stream2); return 1; }
-    if (download_lf(ctx, ctx->out, denoised_out, sai_mask, asize, each)) return 1;
-    CK(cudaStreamSynchronize(ctx->stream2));
-    return 0;
+    return step_host(ctx, 2, p, noisy_io, basic_io, sai_mask, denoised_out);
 }
 
 int lfbm3d_run(lfbm5d_ctx *ctx, const lfbm3d_params *p, float *const *noisy_io, const unsigned *sai_mask, float *const *basic_out,

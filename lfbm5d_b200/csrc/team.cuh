@@ -377,11 +377,18 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
     if (T->comm) TMARK(3);
     {   // ---- exchange: disparity maps to everybody, partial candidate lists to the owners of the reference rows ----
         std::vector<TeamSeg> segs;
+        // a rank reads the disparity maps at the self matches of its own reference rows only: rows within nSim of them
         for (int g = 0; g < G; g++)
             for (int s = share[g].s0; s < share[g].s1; s++) {
                 const int st = P0.stereo_sai[s];
-                segs.push_back({ g, -1, TB_FIRST, TB_FIRST, (size_t) st * plane * 4, (size_t) st * plane * 4, plane * 4 });
-                segs.push_back({ g, -1, TB_SHAPE, TB_SHAPE, (size_t) st * plane, (size_t) st * plane, plane });
+                for (int h = 0; h < G; h++) {
+                    const Band &bh = T->bands[h];
+                    if (h == g || bh.a1 <= bh.a0) continue;
+                    const int ylo = std::max(0, pc.rows[bh.a0] - (int) pc.nSim), yhi = std::min((int) pc.hb, pc.rows[bh.a1 - 1] + (int) pc.nSim + 1);
+                    const size_t o = (size_t) st * plane + (size_t) ylo * wb, nb = (size_t) (yhi - ylo) * wb;
+                    segs.push_back({ g, h, TB_FIRST, TB_FIRST, o * 4, o * 4, nb * 4 });
+                    segs.push_back({ g, h, TB_SHAPE, TB_SHAPE, o, o, nb });
+                }
             }
         if (pg.nself > 0)
             for (int g = 0; g < G; g++)
