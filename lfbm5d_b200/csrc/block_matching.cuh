@@ -314,12 +314,16 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
 // plane p over the current 32. k_sat2 then starts every strip from these values instead of waiting for the strip to its left.
 #define SATE_NT 256
 #define SATE_B 32
+// dynamic shared memory of k_sat_edges: two difference buffers + the img1 / img2 source tiles
+inline size_t sate_smem(int k) { return ((size_t) 2 * (SATE_B + k) * k * 16 + (size_t) (SATE_B + k) * k + (size_t) (SATE_B + k + 16) * (k + 16)) * 4; }
 template <bool SELF, int K>
 __global__ void __launch_bounds__(SATE_NT) k_sat_edges(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
                                                        float *__restrict__ frow, float *__restrict__ fcol)
 {
-    extern __shared__ float s_d[];                 // two buffers of [SATE_B + K][K][16] squared differences
+    extern __shared__ float s_d[];                 // two buffers of [SATE_B + K][K][16] squared differences, then the source tiles
     constexpr int NA = SATE_B + K, BUF = NA * K * 16;
+    constexpr int T2A = NA + 16, T2C = K + 16;     // img2 tile: room for the 14 column offsets of a group along x
+    float *T1 = s_d + 2 * BUF, *T2 = T1 + NA * K;  // img1 tile [a][c]; img2 tile [a2][c2]
     const SatGroup G = groups[blockIdx.x];
     const int dir = blockIdx.y;                    // 0: first row (scan along x), 1: first column (scan along y)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -327,29 +331,39 @@ __global__ void __launch_bounds__(SATE_NT) k_sat_edges(SatGeom g, const SatGroup
     const int end = dir == 0 ? g.col_end : g.row_end;
     const int nblk = (end - lo - 1 + SATE_B - 1) / SATE_B;      // positions lo + 1 .. end - 1; at least one block (first patch)
     const int pl = tid & 15;
-    const int ox = pl < G.nplanes ? planes[G.first_plane + pl].ox : 0;
+    const int e = pl < G.nplanes ? planes[G.first_plane + pl].ox - G.oxmin : 0;      // column shift of the lane's plane inside the img2 tile
     const float *__restrict__ i1 = G.img1, *__restrict__ i2 = G.img2;
-    // squared differences of block b: along positions a0 .. a0 + NA - 1 (a0 = lo + b * SATE_B), across lo .. lo + K - 1
-    auto produce = [&](int b, int first_thread, int nthreads) {
+    // squared differences of block b: along positions a0 .. a0 + NA - 1 (a0 = lo + b * SATE_B), across lo .. lo + K - 1.
+    // The source pixels are staged first (coalesced, all loads of a thread in flight; pixels outside the image read as 0 like the
+    // zero fill of k_sat2's row rings), then every (position, plane) difference comes from shared memory.
+    auto produce = [&](int b, int first_thread, int nthreads, int barrier_id) {
         float *D = s_d + (b & 1) * BUF;
-        const int a0 = lo + b * SATE_B;
-        for (int t = tid - first_thread; t < NA * K * 16; t += nthreads) {
+        const int a0 = lo + b * SATE_B, t0 = tid - first_thread;
+        const int n2a = dir == 0 ? T2A : NA, n2c = dir == 0 ? K : T2C;
+        for (int t = t0; t < NA * K; t += nthreads) {
+            const int a = dir == 0 ? t % NA : t / K, c = dir == 0 ? t / NA : t % K;
+            const int y = dir == 0 ? lo + c : a0 + a, x = dir == 0 ? a0 + a : lo + c;
+            T1[a * K + c] = (y < h && x < w) ? __ldg(i1 + (size_t) y * w + x) : 0.f;
+        }
+        for (int t = t0; t < n2a * n2c; t += nthreads) {
+            const int a = dir == 0 ? t % n2a : t / n2c, c = dir == 0 ? t / n2a : t % n2c;
+            const int y = (dir == 0 ? lo + c : a0 + a) + G.oy, x = (dir == 0 ? a0 + a : lo + c) + G.oxmin;
+            T2[a * T2C + c] = (y >= 0 && y < h && x >= 0 && x < w) ? __ldg(i2 + (size_t) y * w + x) : 0.f;
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nthreads) : "memory");
+        for (int t = t0; t < NA * K * 16; t += nthreads) {
             const int ac = t >> 4, a = ac / K, c = ac - a * K;
             if (pl >= G.nplanes) continue;
-            const int y = dir == 0 ? lo + c : a0 + a, x = dir == 0 ? a0 + a : lo + c;
-            float v = 0.f;
-            if (y < h) {       // pixels outside the image read as 0 (like the zero fill of k_sat2's row rings)
-                const float p1 = x < w ? __ldg(i1 + (size_t) y * w + x) : 0.f;
-                const int yy = y + G.oy, xx = x + ox;
-                const float p2 = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(i2 + (size_t) yy * w + xx) : 0.f;
-                const float df = p2 - p1;
-                v = df * df;
-                if (SELF) { if (y >= g.ylim || x >= g.xlim) v = 0.f; }
+            const float df = (dir == 0 ? T2[(a + e) * T2C + c] : T2[a * T2C + c + e]) - T1[a * K + c];
+            float v = df * df;
+            if (SELF) {
+                const int y = dir == 0 ? lo + c : a0 + a, x = dir == 0 ? a0 + a : lo + c;
+                if (y >= g.ylim || x >= g.xlim) v = 0.f;
             }
             D[t] = v;
         }
     };
-    produce(0, 0, SATE_NT);
+    produce(0, 0, SATE_NT, 1);
     __syncthreads();
     float s = 0.0f;
     float *out = nullptr;
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(SATE_NT) k_sat_edges(SatGeom g, const SatGroup
                     out[p0 + q] = s;
                 }
             }
-        } else if (b + 1 < nblk) produce(b + 1, 32, SATE_NT - 32);
+        } else if (b + 1 < nblk) produce(b + 1, 32, SATE_NT - 32, 2);
         __syncthreads();
     }
 }

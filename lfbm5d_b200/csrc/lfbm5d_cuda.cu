@@ -592,7 +592,7 @@ int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg
     auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
     auto kedge = pc.k == 8 ? k_sat_edges<true, 8> : k_sat_edges<true, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const size_t smem_e = (size_t) 2 * (SATE_B + pc.k) * pc.k * 16 * 4;
+    const size_t smem_e = sate_smem((int) pc.k);
     CK(cudaFuncSetAttribute((const void *) kedge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_e));
     kedge<<<dim3(sg1 - sg0, 2), SATE_NT, smem_e, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), ctx->frow.as<float>(), ctx->fcol.as<float>());
     ctx->stats.kernel_launches++;
@@ -617,7 +617,7 @@ int launch_sat_stereo(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int 
     auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
     auto kedge = pc.k == 8 ? k_sat_edges<false, 8> : k_sat_edges<false, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    const size_t smem_e = (size_t) 2 * (SATE_B + pc.k) * pc.k * 16 * 4;
+    const size_t smem_e = sate_smem((int) pc.k);
     CK(cudaFuncSetAttribute((const void *) kedge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_e));
     kedge<<<dim3(ngroups, 2), SATE_NT, smem_e, strm>>>(g, P.d_groups.as<SatGroup>() + P.nself_groups + s0 * P.groups_per_slot, P.d_planes.as<SatPlane>(),
                                                        ctx->frow.as<float>(), ctx->fcol.as<float>());

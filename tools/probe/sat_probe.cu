@@ -90,7 +90,7 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
         CK(cudaMemset(prog, 0, pbytes));
         CK(cudaEventRecord(e0));
         {
-            const size_t smem_e = (size_t) 2 * (SATE_B + K) * K * 16 * 4;
+            const size_t smem_e = sate_smem(K);
             CK(cudaFuncSetAttribute((const void *) k_sat_edges<SELF, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_e));
             k_sat_edges<SELF, K><<<dim3((int) groups.size(), 2), SATE_NT, smem_e>>>(g, dg, dp, frow, fcol);
         }
