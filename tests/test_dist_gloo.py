@@ -100,3 +100,45 @@ def _window_all(w, prm):
         for t in range(int(w[3]), int(w[3]) + 3):
             out.append(s * int(prm.awidth) + t if int(prm.ang_major) == L.ROWMAJOR else s + t * int(prm.aheight))
     return out
+
+
+def _band_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import lfbm5d_b200 as L
+    p1 = L.make_params(10.0, 2.7, 17, 17, 1, 1024, 1024, 3, 8, 18, 6, 16, 4, L.ID, L.SADCT, L.HAAR)
+    mine = torch.tensor(L.plan_band(world, rank, 1, p1), dtype=torch.int64)
+    allb = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    ret[rank] = [tuple(int(x) for x in b) for b in allb]
+    dist.destroy_process_group()
+
+
+def test_team_bands_tile_the_light_field():
+    """Row bands of the team path (lfbm5d_team_plan_band; csrc/team.cuh): for every world size the owned interior rows tile [0, H)
+    in rank order, every rank keeps its band plus the rows it shares with the next rank (halo = 2 n + k - p rows), ranks that would
+    break the two-ranks-per-pixel-row rule get nothing. Host logic only (no GPU); the world-2 part runs over gloo."""
+    import lfbm5d_b200 as L
+    for (H, k, N, t2) in ((1024, 16, 8, L.ID), (1024, 8, 16, L.DCT), (256, 16, 8, L.ID), (434, 8, 8, L.DCT)):
+        prm = L.make_params(10.0, 2.7, 17, 17, 1, 640, H, 3, N, 18, 6, k, 4, t2, L.SADCT, L.HAAR)
+        for world in (1, 2, 3, 4, 8, 16):
+            bands = [L.plan_band(world, r, 1, prm) for r in range(world)]
+            assert bands[0][0] == 0
+            active = [b for b in bands if b[1] > b[0]]
+            assert active and active[-1][1] == H
+            for a, b in zip(bands[:-1], bands[1:]):
+                assert a[1] == b[0] or b[1] == b[0]                      # contiguous in rank order (idle ranks own nothing)
+            for b in active[:-1]:
+                assert b[2] - b[1] == 2 * 24 + k - 4 or b[2] == H        # rows shared with the next rank: 2 n + k - p (search radius each way + patch)
+            if H == 256:
+                assert len(active) <= 4                                   # 61 reference rows: at most 4 ranks get rows
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, 29617, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] == ret[1] and ret[0][0][0] == 0 and ret[0][0][1] == ret[0][1][0] and ret[0][1][1] == 1024
