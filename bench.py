@@ -25,6 +25,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # team lanes: concurrent streams must not share a hardware queue
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -175,6 +177,8 @@ def run_ours(args):
     if world > 1:
         from lfbm5d_b200 import dist as D
         team = D.make_team(eng, dist, dev)
+        if args.lanes > 1:
+            team.set_lanes(args.lanes)
     torch.cuda.synchronize()
 
     def one_step():
@@ -212,14 +216,17 @@ def run_ours(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = tmax.clone()
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        ms, launches = float(tm[0].item()), int(ts[1].item())
+        ms = float(tm[0].item())
+        tl = torch.tensor([float(team.launches())], device=dev, dtype=torch.float64)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl.item())
     ms_per_step = ms / args.steps
     frac_passes = 1.0 if not args.passes else args.passes / float(N_PASSES)
     value = lf_pix * frac_passes / (ms_per_step * 1e-3) / 1e6
     team_info = None
     if team is not None:
         tst = team.stats()
-        team_info = {"nvlink_bytes_sent_per_rank_per_step": (tst["bytes_exchanged"] - bytes0) / args.steps, "peer_view": tst["peer_view"],
+        team_info = {"lanes": args.lanes, "nvlink_bytes_sent_per_rank_per_step": (tst["bytes_exchanged"] - bytes0) / args.steps, "peer_view": tst["peer_view"],
                      "passes_redone": tst["passes_redone"], "band_rows_rank0": team.band(0)}
 
     # quality of the timed output: PSNR against the clean LF (utilities.cpp:412-435, mean over the SAIs)
@@ -539,6 +546,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--passes", type=int, default=0, help="debug: stop each step after this many window passes (value is scaled)")
     ap.add_argument("--profile-passes", type=int, default=4)
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("LFBM5D_LANES", "3")),
+                    help="N > 1: independent windows of a plan level run concurrently, one per lane (own pass buffers, ~22 GB each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -125,6 +125,12 @@ int  lfbm5d_team_unique_id(char *id128);
 int  lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int world, const char *id128);
 void lfbm5d_team_destroy(lfbm5d_team *team);
 int  lfbm5d_team_local_ranks(lfbm5d_team *team);      /* emulated: world; NCCL: 1 */
+/* Lanes (>= 1, default 1): the windows of a step form a static plan whose levels hold windows that share no SAI (lfbm5d_step_plan);
+ * with n lanes up to n windows of a level run concurrently, each on its own contexts (pass buffers) and exchange state but on the
+ * same light field, so that the latency-bound parts of one window pass hide behind the bandwidth-bound parts of another. Results
+ * do not change (windows of a level commute). */
+int  lfbm5d_team_set_lanes(lfbm5d_team *team, int nlanes);
+unsigned long long lfbm5d_team_launches(lfbm5d_team *team);   /* kernels launched by all contexts of the team since their stats were reset */
 /* One step (1 or 2) of ONE light field on the whole team. d_*: arrays of lfbm5d_team_local_ranks() device pointers, one replica of the
  * light field per local rank ([asize][chnls][height][width] floats, as for lfbm5d_step{1,2}_device). A rank reads and colour-transforms
  * only the rows of its band (+ halo) of d_noisy_io / d_basic_io; on return d_out[l] holds the rows [row_lo, keep_hi) of lfbm5d_team_band

@@ -47,7 +47,7 @@ EXPORTS = ["lfbm5d_create", "lfbm5d_destroy", "lfbm5d_last_error", "lfbm5d_reset
            "lfbm5d_debug_schedule", "lfbm5d_step_begin", "lfbm5d_step_window", "lfbm5d_step_end", "lfbm5d_step_accumulators",
            "lfbm5d_step_plan", "lfbm5d_step_force_sadct", "lfbm5d_step_window_ex", "lfbm5d_debug_block_matching", "lfbm5d_team_create_emulated", "lfbm5d_team_unique_id",
            "lfbm5d_team_create_nccl", "lfbm5d_team_destroy", "lfbm5d_team_local_ranks", "lfbm5d_team_step", "lfbm5d_team_band",
-           "lfbm5d_team_stats", "lfbm5d_team_disable_peer_view", "lfbm5d_team_timing", "lfbm5d_team_plan_band", "lfbm5d_copy_rows", "lfbm5d_sync", "lfbm5d_team_use_peer_exchange"]
+           "lfbm5d_team_stats", "lfbm5d_team_disable_peer_view", "lfbm5d_team_timing", "lfbm5d_team_plan_band", "lfbm5d_copy_rows", "lfbm5d_sync", "lfbm5d_team_use_peer_exchange", "lfbm5d_team_set_lanes", "lfbm5d_team_launches"]
 
 HOST_LIB_PATH = os.path.join(_HERE, "_lib", "liblfbm5d_host.so")
 HOST_EXPORTS = ["lfio_add_noise", "lfio_psnr"]           # include/lfbm5d_host_c.h
@@ -392,6 +392,15 @@ class Team(object):
         out = (C.c_float * 12)()
         self.lib.lfbm5d_team_timing(self.handle, int(on), out)
         return [float(x) for x in out]
+
+    def set_lanes(self, n):
+        """n windows of a plan level run concurrently (each lane: own pass buffers); results do not change."""
+        if self.lib.lfbm5d_team_set_lanes(self.handle, int(n)) != 0:
+            raise RuntimeError("lfbm5d_team_set_lanes: " + self.lib.lfbm5d_last_error().decode())
+
+    def launches(self):
+        self.lib.lfbm5d_team_launches.restype = C.c_ulonglong
+        return int(self.lib.lfbm5d_team_launches(self.handle))
 
     def use_peer_exchange(self, on=True):
         self.lib.lfbm5d_team_use_peer_exchange(self.handle, int(on))

@@ -33,17 +33,19 @@ int fail(const std::string &m) { g_err = m; return 1; }
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;      // an alias of another context's allocation (lanes of a team share the accumulators of the light field)
+    void borrow(const DevBuf &o) { release(); p = o.p; cap = o.cap; borrowed = true; }
     int ensure(size_t bytes)
     {
         if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (p && !borrowed) cudaFree(p);
+        p = nullptr; cap = 0; borrowed = false;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e != cudaSuccess) return fail(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
         cap = bytes;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 

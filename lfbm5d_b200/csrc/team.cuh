@@ -32,6 +32,8 @@ struct Band {
     int j0 = 0, j1 = 0;          // interior rows of [y0, c1): what the rank keeps up to date of num / den
 };
 
+struct PlaneShare { int s0, s1, sg0, sg1, pl0, pl1; };      // disparity slots, self groups and self planes of a rank in a pass
+
 enum TeamBuf { TB_EST0, TB_FIRST, TB_SHAPE, TB_PKEY_SEND, TB_PKEY_ALL, TB_PCNT_SEND, TB_PCNT_ALL, TB_NUMSYM, TB_DENSYM, TB_COUNTERS,
                TB_S_AT, TB_S_MIR, TB_GSEND, TB_GRECV, TB_NBUF };
 
@@ -98,6 +100,10 @@ struct lfbm5d_team {
     unsigned cparity = 0;                          // which half of the counter buffers the next counter exchange uses
     DevBuf xsegs, xflags, xdone, xflagptrs;
     bool use_peer_exchange = true;
+    struct { LfWindow win; int pst = 0, cst = 0; bool partial = false; std::vector<PlaneShare> share; } pw;      // pass in flight
+    struct { LfWindow win; unsigned cst_asw = 0, pst_asw = 0, n_unproc = 0, max_unproc = 0, calls = 0; int min_s = 0, min_t = 0; bool open = false; } wf;   // window in flight
+    std::vector<lfbm5d_team *> lanes;             // further lanes of this team: own contexts and exchange state, the same light field
+    bool is_lane = false;
     unsigned long long tie_patches = 0;
     // per-phase device time of local rank 0 (lfbm5d_team_timing): events at the phase boundaries of a pass
     bool timing = false;
@@ -182,7 +188,7 @@ int team_exchange_peer(lfbm5d_team *T, const std::vector<TeamSeg> &segs)
     const unsigned grid = (unsigned) std::max<unsigned long long>(1, std::min<unsigned long long>(chunks, (unsigned long long) ctx->num_sms * 8));
     k_peer_copy<<<grid, 256, 0, ctx->stream>>>(T->xsegs.as<PeerSegD>(), (int) d.size(), (unsigned) chunks, T->xdone.as<unsigned>(),
                                                T->xflagptrs.as<unsigned *>(), me, G, epoch);
-    k_peer_wait<<<1, 32, 0, ctx->stream>>>(T->xflags.as<unsigned>(), me, G, epoch);
+    k_peer_wait<<<1, 32, 0, ctx->stream>>>(T->xflags.as<unsigned>(), me, G, epoch, T->xdone.as<unsigned>() + 8);
     ctx->stats.kernel_launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -267,7 +273,6 @@ std::vector<Band> team_bands(const PassCfg &pc, int G)
 
 // Deal the offset planes of a pass out: disparity slots evenly (whole SAIs: their argmin needs all 169 planes), then the self
 // groups in contiguous runs so that every rank ends up with about the same number of planes.
-struct PlaneShare { int s0, s1, sg0, sg1, pl0, pl1; };
 std::vector<PlaneShare> team_planes(const SatPlan &P, int G)
 {
     std::vector<PlaneShare> S(G);
@@ -307,17 +312,19 @@ size_t cslot(const lfbm5d_team *T, int g) { return ((size_t) T->cparity * T->wor
 
 #define TMARK(i) do { if (T->timing) CK(cudaEventRecord(T->tev[i], T->local[0]->stream)); } while (0)
 
-// ---- one core call of the team (all ranks in lockstep; `pst == cst` or the partial-window branch) ----
-// Returns through *cov the number of covered entries of LF_denoised_percent (summed over the ranks).
-int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, int cst, unsigned long long *cov)
+// ---- one core call of the team, in pieces (a lane enqueues bm + body and reads the counters later) ----
+// block matching of the own planes + exchange of the match tables
+int team_pass_bm(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, int cst)
 {
     const bool partial = cst >= 0 && cst != pst;
+    T->pw.win = win; T->pw.pst = pst; T->pw.cst = cst; T->pw.partial = partial;
     const int G = T->world, nl = (int) T->local.size();
     const PassGeom pg = pass_geom(pc);
     const size_t plane = pg.plane, NM = pc.N + 1;
     const int C = (int) pc.C, wb = (int) pc.wb;
     std::vector<SatPlan *> plans(nl);
-    std::vector<PlaneShare> share;
+    std::vector<PlaneShare> &share = T->pw.share;
+    share.clear();
     TMARK(2);
     // ---- block matching: own planes ----
     for (int l = 0; l < nl; l++) {
@@ -400,158 +407,195 @@ int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, i
                 }
         if (team_exchange(T, segs)) return 1;
     }
-    bool redo = false;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        TMARK(4);
-        // ---- merged selection, groups and the first part of the aggregation: rows [pc1, c1) ----
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            const int g = T->local_rank[l];
-            const Band &bd = T->bands[g];
-            TeamCtxBufs *b = team_bufs(ctx);
-            CK(cudaSetDevice(ctx->device));
-            unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
-            CK(cudaMemsetAsync(cnts, 0, 64, ctx->stream));
-            const int nown = bd.r1 - bd.r0;
-            if (nown > 0) {
-                if (pg.nself > 0 && !redo) {
-                    SelGeom sg{};
-                    sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
-                    sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
-                    void (*km)(SelGeom, int, int, int, const unsigned *, const unsigned long long *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
-                    switch (pc.N) {
-                        case 2: km = k_bm_merge<3>; break;
-                        case 4: km = k_bm_merge<5>; break;
-                        case 8: km = k_bm_merge<9>; break;
-                        case 16: km = k_bm_merge<17>; break;
-                        default: km = k_bm_merge<33>; break;
-                    }
-                    if (ctx->tielist.ensure(((size_t) pg.R + 1) * 4)) return 1;
-                    unsigned *tl = ctx->tielist.as<unsigned>();
-                    // with the peer view the tied patches are redone right here; without it they are only counted (cnts[1]) and the
-                    // team falls back to exchanging the complete sums and redoing the pass
-                    unsigned *tcount = T->peer_ready ? reinterpret_cast<unsigned *>(cnts + 2) : reinterpret_cast<unsigned *>(cnts + 1);
-                    LAUNCH(ctx, km, (nown + 127) / 128, 128, 0, sg, G, bd.r0, bd.r1, b->pcnt_all.as<unsigned>(), b->pkey_all.as<unsigned long long>(),
-                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), T->peer_ready ? tl : (unsigned *) nullptr, tcount);
-                    if (T->peer_ready) {
-                        PeerTable pt{};
-                        pt.G = G;
-                        for (int q = 0; q < G; q++) { pt.s_at[q] = T->peer_at[q]; pt.s_mir[q] = T->peer_mir[q]; pt.pl0[q] = share[q].pl0; }
-                        pt.pl0[G] = share[G - 1].pl1;
-                        LAUNCH(ctx, k_bm_select, std::min<size_t>(nown, (size_t) ctx->num_sms * 16), 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(),
-                               ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl,
-                               (const unsigned *) reinterpret_cast<unsigned *>(cnts + 2), pt);
-                    }
-                } else if (pg.nself > 0) {      // ties somewhere: every rank now holds the complete sums, the reference's selection as on one GPU
-                    if (launch_self_select(ctx, pc, ctx->stream)) return 1;
-                } else
-                    LAUNCH(ctx, k_bm_identity_rows, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, wb, bd.r0, bd.r1, (int) pc.N,
-                           ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
-                if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure((size_t) pg.R * 2)) return 1;
-                LAUNCH(ctx, k_group_masks, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, bd.r0, bd.r1, wb, (unsigned) plane,
-                       (int) pc.A, pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
-                if (clear_zero_blocks(ctx, pc) || launch_groups(ctx, pc, win, pst, partial, bd.r0, bd.r1)) return 1;
-                if (launch_aggregate(ctx, pc, win, bd.pc1, bd.c1, bd.a0, bd.a1)) return 1;
-            }
-        }
-        TMARK(5);
-        {   // rows O_g = [y1, c1) go to the next rank, which continues the sums
-            std::vector<TeamSeg> segs;
-            for (int g = 0; g + 1 < G; g++) {
-                const Band &bd = T->bands[g];
-                if (bd.c1 <= bd.y1) continue;
-                for (int a = 0; a < (int) pc.A; a++) {
-                    if (!win.mask[a] || win.proc[a]) continue;
-                    for (int c = 0; c < C; c++) {
-                        const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y1 * wb) * 4, bytes = (size_t) (bd.c1 - bd.y1) * wb * 4;
-                        segs.push_back({ g, g + 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
-                        segs.push_back({ g, g + 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
-                    }
+    return 0;
+}
+
+// merged selection, groups, both parts of the aggregation and the border exchanges of a pass (enqueue only, no host sync)
+int team_pass_body(lfbm5d_team *T, const PassCfg &pc, bool redo)
+{
+    const LfWindow &win = T->pw.win;
+    const int pst = T->pw.pst;
+    const bool partial = T->pw.partial;
+    const std::vector<PlaneShare> &share = T->pw.share;
+    const int G = T->world, nl = (int) T->local.size();
+    const PassGeom pg = pass_geom(pc);
+    const size_t plane = pg.plane;
+    const int C = (int) pc.C, wb = (int) pc.wb;
+    TMARK(4);
+    // ---- merged selection, groups and the first part of the aggregation: rows [pc1, c1) ----
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const int g = T->local_rank[l];
+        const Band &bd = T->bands[g];
+        TeamCtxBufs *b = team_bufs(ctx);
+        CK(cudaSetDevice(ctx->device));
+        unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
+        CK(cudaMemsetAsync(cnts, 0, 64, ctx->stream));
+        const int nown = bd.r1 - bd.r0;
+        if (nown > 0) {
+            if (pg.nself > 0 && !redo) {
+                SelGeom sg{};
+                sg.w = pc.wb; sg.nSim = pc.nSim; sg.Ns = pg.Ns; sg.N = pc.N; sg.R = pg.R; sg.nc = pg.nc; sg.threshold = pg.threshold;
+                sg.rows = ctx->rows.as<int>(); sg.cols = ctx->cols.as<int>();
+                void (*km)(SelGeom, int, int, int, const unsigned *, const unsigned long long *, unsigned *, unsigned *, unsigned *, unsigned *) = nullptr;
+                switch (pc.N) {
+                    case 2: km = k_bm_merge<3>; break;
+                    case 4: km = k_bm_merge<5>; break;
+                    case 8: km = k_bm_merge<9>; break;
+                    case 16: km = k_bm_merge<17>; break;
+                    default: km = k_bm_merge<33>; break;
                 }
-            }
-            if (team_exchange(T, segs)) return 1;
-        }
-        TMARK(6);
-        // ---- second part of the aggregation: rows [y0, pc1) on top of the previous rank's sums; coverage and tie counts ----
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            const int g = T->local_rank[l];
-            const Band &bd = T->bands[g];
-            TeamCtxBufs *b = team_bufs(ctx);
-            CK(cudaSetDevice(ctx->device));
-            if (bd.r1 > bd.r0 && launch_aggregate(ctx, pc, win, bd.y0, bd.pc1, bd.a0, bd.a1)) return 1;
-            unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
-            if (bd.i1 > bd.i0)
-                LAUNCH(ctx, k_count_cov_rows, grid_for(ctx, (size_t) pc.A * C * (bd.i1 - bd.i0) * pc.W), 256, 0, ctx->densym.as<float>(), win, (int) pc.W, (int) pc.H,
-                       C, (int) pc.n, (int) pc.k, bd.i0, bd.i1 - bd.i0, cnts);
-        }
-        TMARK(7);
-        {   // final rows [y0, pc1) back to the previous rank (its replica of O_{g-1}); counters to everybody
-            std::vector<TeamSeg> segs;
-            for (int g = 1; g < G; g++) {
-                const Band &bd = T->bands[g];
-                if (bd.pc1 <= bd.y0) continue;
-                for (int a = 0; a < (int) pc.A; a++) {
-                    if (!win.mask[a] || win.proc[a]) continue;
-                    for (int c = 0; c < C; c++) {
-                        const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y0 * wb) * 4, bytes = (size_t) (bd.pc1 - bd.y0) * wb * 4;
-                        segs.push_back({ g, g - 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
-                        segs.push_back({ g, g - 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
-                    }
+                if (ctx->tielist.ensure(((size_t) pg.R + 1) * 4)) return 1;
+                unsigned *tl = ctx->tielist.as<unsigned>();
+                // with the peer view the tied patches are redone right here; without it they are only counted (cnts[1]) and the
+                // team falls back to exchanging the complete sums and redoing the pass
+                unsigned *tcount = T->peer_ready ? reinterpret_cast<unsigned *>(cnts + 2) : reinterpret_cast<unsigned *>(cnts + 1);
+                LAUNCH(ctx, km, (nown + 127) / 128, 128, 0, sg, G, bd.r0, bd.r1, b->pcnt_all.as<unsigned>(), b->pkey_all.as<unsigned long long>(),
+                       ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), T->peer_ready ? tl : (unsigned *) nullptr, tcount);
+                if (T->peer_ready) {
+                    PeerTable pt{};
+                    pt.G = G;
+                    for (int q = 0; q < G; q++) { pt.s_at[q] = T->peer_at[q]; pt.s_mir[q] = T->peer_mir[q]; pt.pl0[q] = share[q].pl0; }
+                    pt.pl0[G] = share[G - 1].pl1;
+                    LAUNCH(ctx, k_bm_select, std::min<size_t>(nown, (size_t) ctx->num_sms * 16), 32, (size_t) pg.Ns * pg.Ns * 8, sg, ctx->s_at.as<float>(),
+                           ctx->s_mir.as<float>(), ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>(), (const unsigned *) tl,
+                           (const unsigned *) reinterpret_cast<unsigned *>(cnts + 2), pt);
                 }
-            }
-            for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, cslot(T, g), cslot(T, g), 24 });
-            if (team_exchange(T, segs)) return 1;
+            } else if (pg.nself > 0) {      // ties somewhere: every rank now holds the complete sums, the reference's selection as on one GPU
+                if (launch_self_select(ctx, pc, ctx->stream)) return 1;
+            } else
+                LAUNCH(ctx, k_bm_identity_rows, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, wb, bd.r0, bd.r1, (int) pc.N,
+                       ctx->bmcount.as<unsigned>(), ctx->bmidx.as<unsigned>());
+            if (ensure_shape_lut(ctx, pc.asw) || ctx->gmask.ensure((size_t) pg.R * 2)) return 1;
+            LAUNCH(ctx, k_group_masks, (nown + 255) / 256, 256, 0, ctx->rows.as<int>(), ctx->cols.as<int>(), pg.nc, bd.r0, bd.r1, wb, (unsigned) plane,
+                   (int) pc.A, pst, win, ctx->shape.as<unsigned char>(), ctx->gmask.as<unsigned short>());
+            if (clear_zero_blocks(ctx, pc) || launch_groups(ctx, pc, win, pst, partial, bd.r0, bd.r1)) return 1;
+            if (launch_aggregate(ctx, pc, win, bd.pc1, bd.c1, bd.a0, bd.a1)) return 1;
         }
-        TMARK(8);
-        // ---- every rank reads the same counters and takes the same decision ----
-        unsigned long long total_cov = 0, total_ties = 0;
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            CK(cudaSetDevice(ctx->device));
-            std::vector<unsigned long long> h((size_t) G * TSLOT_U64);
-            CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.as<char>() + cslot(T, 0), h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (l == 0)
-                for (int g = 0; g < G; g++) {
-                    total_cov += h[(size_t) g * TSLOT_U64]; total_ties += h[(size_t) g * TSLOT_U64 + 1] & 0xffffffffull;
-                    T->tie_patches += h[(size_t) g * TSLOT_U64 + 2] & 0xffffffffull;
-                }
-            ctx->stats.window_passes++;
-        }
-        T->cparity ^= 1u;
-        *cov = total_cov;
-        if (T->timing) {    // phases 2..8: block matching, exchange, selection + groups + aggregation, exchange, aggregation 2, exchange
-            for (int i = 2; i < 8; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
-            // inside block matching: self planes, partial selection (main stream); disparity planes, argmin (second stream)
-            const int pairs[4][2] = { { 0, 1 }, { 1, 2 }, { 0, 3 }, { 3, 4 } };
-            for (int i = 0; i < 4; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->bev[pairs[i][0]], T->bev[pairs[i][1]]) == cudaSuccess) T->phase_ms[8 + i] += ms; }
-        }
-        if (total_ties == 0 || redo) break;
-        // Exact float ties among the selected distances of some reference patch: the reference's result then depends on its heap
-        // algorithm over the complete candidate sequence. Redo the pass from the padded accumulators with the complete sums on
-        // every rank (the planes are still there: only their exchange, the selection, the groups and the aggregation run again).
-        redo = true;
-        T->passes_redone++;
+    }
+    TMARK(5);
+    {   // rows O_g = [y1, c1) go to the next rank, which continues the sums
         std::vector<TeamSeg> segs;
-        for (int g = 0; g < G; g++) {
-            const size_t off = (size_t) share[g].pl0 * pg.R * 4, bytes = (size_t) (share[g].pl1 - share[g].pl0) * pg.R * 4;
-            segs.push_back({ g, -1, TB_S_AT, TB_S_AT, off, off, bytes });
-            segs.push_back({ g, -1, TB_S_MIR, TB_S_MIR, off, off, bytes });
+        for (int g = 0; g + 1 < G; g++) {
+            const Band &bd = T->bands[g];
+            if (bd.c1 <= bd.y1) continue;
+            for (int a = 0; a < (int) pc.A; a++) {
+                if (!win.mask[a] || win.proc[a]) continue;
+                for (int c = 0; c < C; c++) {
+                    const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y1 * wb) * 4, bytes = (size_t) (bd.c1 - bd.y1) * wb * 4;
+                    segs.push_back({ g, g + 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
+                    segs.push_back({ g, g + 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
+                }
+            }
         }
         if (team_exchange(T, segs)) return 1;
-        for (int l = 0; l < nl; l++) {      // restore the accumulators of the window on the rows the pass wrote
-            lfbm5d_ctx *ctx = T->local[l];
-            const Band &bd = T->bands[T->local_rank[l]];
-            CK(cudaSetDevice(ctx->device));
-            if (bd.c1 > bd.y0)
-                LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) pc.A * (bd.c1 - bd.y0) * wb), 256, 0, T->d_noisy[l], pc.step == 2 ? T->d_basic[l] : (const float *) nullptr,
-                       ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
-                       ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.W, (int) pc.H, C, (int) pc.n, bd.y0, bd.c1 - bd.y0, bd.y1);
+    }
+    TMARK(6);
+    // ---- second part of the aggregation: rows [y0, pc1) on top of the previous rank's sums; coverage and tie counts ----
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const int g = T->local_rank[l];
+        const Band &bd = T->bands[g];
+        TeamCtxBufs *b = team_bufs(ctx);
+        CK(cudaSetDevice(ctx->device));
+        if (bd.r1 > bd.r0 && launch_aggregate(ctx, pc, win, bd.y0, bd.pc1, bd.a0, bd.a1)) return 1;
+        unsigned long long *cnts = reinterpret_cast<unsigned long long *>(b->counters.as<char>() + cslot(T, g));
+        if (bd.i1 > bd.i0)
+            LAUNCH(ctx, k_count_cov_rows, grid_for(ctx, (size_t) pc.A * C * (bd.i1 - bd.i0) * pc.W), 256, 0, ctx->densym.as<float>(), win, (int) pc.W, (int) pc.H,
+                   C, (int) pc.n, (int) pc.k, bd.i0, bd.i1 - bd.i0, cnts);
+    }
+    TMARK(7);
+    {   // final rows [y0, pc1) back to the previous rank (its replica of O_{g-1}); counters to everybody
+        std::vector<TeamSeg> segs;
+        for (int g = 1; g < G; g++) {
+            const Band &bd = T->bands[g];
+            if (bd.pc1 <= bd.y0) continue;
+            for (int a = 0; a < (int) pc.A; a++) {
+                if (!win.mask[a] || win.proc[a]) continue;
+                for (int c = 0; c < C; c++) {
+                    const size_t off = (((size_t) a * C + c) * plane + (size_t) bd.y0 * wb) * 4, bytes = (size_t) (bd.pc1 - bd.y0) * wb * 4;
+                    segs.push_back({ g, g - 1, TB_NUMSYM, TB_NUMSYM, off, off, bytes });
+                    segs.push_back({ g, g - 1, TB_DENSYM, TB_DENSYM, off, off, bytes });
+                }
+            }
         }
-        // est0 was overwritten on the own rows by k_pad_rows with the same values (num / den of the light field are unchanged)
+        for (int g = 0; g < G; g++) segs.push_back({ g, -1, TB_COUNTERS, TB_COUNTERS, cslot(T, g), cslot(T, g), 24 });
+        if (team_exchange(T, segs)) return 1;
+    }
+    TMARK(8);
+    return 0;
+}
+
+// every rank reads the same counters (host sync) and takes the same decisions from them
+int team_pass_read(lfbm5d_team *T, unsigned long long *cov, unsigned long long *ties)
+{
+    const int G = T->world, nl = (int) T->local.size();
+    // ---- every rank reads the same counters and takes the same decision ----
+    unsigned long long total_cov = 0, total_ties = 0;
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        CK(cudaSetDevice(ctx->device));
+        std::vector<unsigned long long> h((size_t) G * TSLOT_U64);
+        CK(cudaMemcpyAsync(h.data(), team_bufs(ctx)->counters.as<char>() + cslot(T, 0), h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (l == 0)
+            for (int g = 0; g < G; g++) {
+                total_cov += h[(size_t) g * TSLOT_U64]; total_ties += h[(size_t) g * TSLOT_U64 + 1] & 0xffffffffull;
+                T->tie_patches += h[(size_t) g * TSLOT_U64 + 2] & 0xffffffffull;
+            }
+        ctx->stats.window_passes++;
+    }
+    T->cparity ^= 1u;
+    *cov = total_cov; *ties = total_ties;
+    if (T->timing) {    // phases 2..8: block matching, exchange, selection + groups + aggregation, exchange, aggregation 2, exchange
+        for (int i = 2; i < 8; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
+        // inside block matching: self planes, partial selection (main stream); disparity planes, argmin (second stream)
+        const int pairs[4][2] = { { 0, 1 }, { 1, 2 }, { 0, 3 }, { 3, 4 } };
+        for (int i = 0; i < 4; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->bev[pairs[i][0]], T->bev[pairs[i][1]]) == cudaSuccess) T->phase_ms[8 + i] += ms; }
     }
     return 0;
+}
+
+// One core call of the team (all ranks in lockstep; `pst == cst` or the partial-window branch), synchronous.
+// Returns through *cov the number of covered entries of LF_denoised_percent (summed over the ranks).
+int team_pass_finish(lfbm5d_team *T, const PassCfg &pc, unsigned long long *cov)
+{
+    unsigned long long ties = 0;
+    if (team_pass_read(T, cov, &ties)) return 1;
+    if (ties == 0) return 0;
+    // Exact float ties among the selected distances of some reference patch while the ranks cannot read each other's sums (no
+    // peer view): the reference's result then depends on its heap algorithm over the complete candidate sequence. Redo the pass
+    // from the padded accumulators with the complete sums on every rank (the planes are still there: only their exchange, the
+    // selection, the groups and the aggregation run again).
+    const int G = T->world, nl = (int) T->local.size();
+    const PassGeom pg = pass_geom(pc);
+    const std::vector<PlaneShare> &share = T->pw.share;
+    const LfWindow &win = T->pw.win;
+    T->passes_redone++;
+    std::vector<TeamSeg> segs;
+    for (int g = 0; g < G; g++) {
+        const size_t off = (size_t) share[g].pl0 * pg.R * 4, bytes = (size_t) (share[g].pl1 - share[g].pl0) * pg.R * 4;
+        segs.push_back({ g, -1, TB_S_AT, TB_S_AT, off, off, bytes });
+        segs.push_back({ g, -1, TB_S_MIR, TB_S_MIR, off, off, bytes });
+    }
+    if (team_exchange(T, segs)) return 1;
+    for (int l = 0; l < nl; l++) {      // restore the accumulators of the window on the rows the pass wrote
+        lfbm5d_ctx *ctx = T->local[l];
+        const Band &bd = T->bands[T->local_rank[l]];
+        CK(cudaSetDevice(ctx->device));
+        if (bd.c1 > bd.y0)
+            LAUNCH(ctx, k_pad_rows, grid_for(ctx, (size_t) pc.A * (bd.c1 - bd.y0) * pc.wb), 256, 0, T->d_noisy[l], pc.step == 2 ? T->d_basic[l] : (const float *) nullptr,
+                   ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
+                   ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.W, (int) pc.H, (int) pc.C, (int) pc.n, bd.y0, bd.c1 - bd.y0, bd.y1);
+    }
+    if (team_pass_body(T, pc, true) || team_pass_read(T, cov, &ties)) return 1;
+    return 0;
+}
+
+int team_pass(lfbm5d_team *T, const PassCfg &pc, const LfWindow &win, int pst, int cst, unsigned long long *cov)
+{
+    if (team_pass_bm(T, pc, win, pst, cst) || team_pass_body(T, pc, false)) return 1;
+    return team_pass_finish(T, pc, cov);
 }
 
 // running estimate of the window on the own rows + its exchange (every rank then holds the complete channel-0 planes)
@@ -663,7 +707,7 @@ int team_peer_setup(lfbm5d_team *T, const PassCfg &pc, int step)
         for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (T->bands[g].i1 - T->bands[g].i0));
         const size_t blk = (size_t) T->ss.asize() * pc.C * maxrows * pc.W * 4;
         TeamCtxBufs *b = team_bufs(ctx);
-        if (b->gsend.ensure(blk) || b->grecv.ensure(blk * G)) return 1;
+        if (!T->is_lane && (b->gsend.ensure(blk) || b->grecv.ensure(blk * G))) return 1;
         return 0;
     };
     if (!T->comm) {      // emulated: all contexts live here
@@ -779,6 +823,25 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
         CK(cudaSetDevice(ctx->device));
         if (setup_tables(ctx, step, p, S.tau_4D) || upload_grid(ctx, S.pc)) return 1;
     }
+    // further lanes: the same step on their own contexts, the accumulators (and the mask) of lane 0
+    for (lfbm5d_team *Tl : T->lanes) {
+        Tl->ss = T->ss;
+        Tl->bands = T->bands; Tl->d_noisy = T->d_noisy; Tl->d_basic = T->d_basic;
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *cl = Tl->local[l], *c0 = T->local[l];
+            CK(cudaSetDevice(cl->device));
+            cl->num.borrow(c0->num); cl->den.borrow(c0->den); cl->mask.borrow(c0->mask);
+            cl->sched.clear();
+        }
+        if (team_peer_setup(Tl, Tl->ss.pc, step)) return 1;
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *cl = Tl->local[l];
+            CK(cudaSetDevice(cl->device));
+            if (setup_tables(cl, step, p, S.tau_4D) || upload_grid(cl, Tl->ss.pc)) return 1;
+        }
+    }
+    if (!T->lanes.empty())      // the colour transform / the cleared accumulators of lane 0's stream, before any lane reads them
+        for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); CK(cudaStreamSynchronize(T->local[l]->stream)); }
     return 0;
 }
 
@@ -810,25 +873,68 @@ int team_select(lfbm5d_team *T, unsigned &ps, unsigned &pt)
     return 0;
 }
 
-// One angular window (bm5d.cpp:204-402), all ranks in lockstep
-int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
+// ---- one angular window (bm5d.cpp:204-402), all ranks in lockstep, in two halves: team_window_begin enqueues everything up to and
+// including the first core call, team_window_finish reads its counters (host sync) and takes the window to its end. A driver
+// with several lanes begins independent windows on all of them before it finishes the first.
+
+// everything of a core call that comes before the counters: choice of pst, running estimate, block matching, groups, aggregation
+int team_window_prepass(lfbm5d_team *T)
+{
+    StepState &S = T->ss;
+    const int step = S.step, nl = (int) T->local.size();
+    PassCfg &pc = S.pc;
+    auto &wf = T->wf;
+    LfWindow &win = wf.win;
+    const unsigned Aw = (unsigned) win.A, C = S.p.chnls;
+    unsigned pst_asw = 0;
+    if (wf.n_unproc == wf.max_unproc && win.mask[wf.cst_asw]) pst_asw = wf.cst_asw;
+    else {      // bm5d.cpp:318-333
+        std::vector<int> items;
+        for (unsigned a = 0; a < Aw; a++) if (win.proc[a] == 0) items.push_back((int) a);
+        std::vector<unsigned long long> hz;
+        if (team_count_zero(T, items, true, pc, hz)) return 1;
+        long long best = -1;
+        for (size_t i = 0; i < items.size(); i++) {
+            const long long z = (long long) (int) hz[i];
+            if (z >= best) { pst_asw = (unsigned) items[i]; best = z; }
+        }
+    }
+    wf.pst_asw = pst_asw;
+    if (wf.calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937), own rows
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            const Band &bd = T->bands[T->local_rank[l]];
+            CK(cudaSetDevice(ctx->device));
+            if (bd.y1 > bd.y0)
+                LAUNCH(ctx, k_est0_rows, grid_for(ctx, (size_t) Aw * (bd.y1 - bd.y0) * pc.wb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
+                       ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.wb, (int) pc.hb, (int) C, bd.y0, bd.y1 - bd.y0);
+        }
+    TMARK(1);
+    if (team_est0_exchange(T, pc, win)) return 1;
+    return team_pass_bm(T, pc, win, (int) pst_asw, (int) wf.cst_asw) || team_pass_body(T, pc, false);
+}
+
+// force_sadct: -1 = sequential rule (sticky dct -> sadct switch, bm5d.cpp:276-280); 0 / 1 = the plan's value for this window
+int team_window_begin(lfbm5d_team *T, unsigned ps, unsigned pt, int force_sadct)
 {
     StepState &S = T->ss;
     const lfbm5d_params *p = &S.p;
     const int step = S.step, nl = (int) T->local.size();
     PassCfg &pc = S.pc;
-    const unsigned asize = S.asize(), asw = 2 * p->an + 1, Aw = asw * asw;
+    const unsigned asw = 2 * p->an + 1, Aw = asw * asw;
     const unsigned C = p->chnls, W = p->width, H = p->height;
-    int cs_asw, min_s, max_s, ct_asw, min_t, max_t;
-    angular_search_window(cs_asw, min_s, max_s, ps, p->aheight, p->an);
-    angular_search_window(ct_asw, min_t, max_t, pt, p->awidth, p->an);
-    const unsigned cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
-    LfWindow win{};
+    auto &wf = T->wf;
+    int cs_asw, max_s, ct_asw, max_t;
+    angular_search_window(cs_asw, wf.min_s, max_s, ps, p->aheight, p->an);
+    angular_search_window(ct_asw, wf.min_t, max_t, pt, p->awidth, p->an);
+    wf.cst_asw = p->ang_major == LFBM5D_ROWMAJOR ? (unsigned) cs_asw * asw + ct_asw : (unsigned) cs_asw + (unsigned) ct_asw * asw;
+    LfWindow &win = wf.win;
+    win = LfWindow{};
     win.A = (int) Aw;
     unsigned n_unproc = 0;
     for (unsigned s_a = 0; s_a < asw; s_a++)
         for (unsigned t_a = 0; t_a < asw; t_a++) {
-            const unsigned s = s_a + min_s, t = t_a + min_t;
+            const unsigned s = s_a + wf.min_s, t = t_a + wf.min_t;
             unsigned st, a;
             if (p->ang_major == LFBM5D_ROWMAJOR) { st = s * p->awidth + t; a = s_a * asw + t_a; }
             else { st = s + t * p->aheight; a = s_a + t_a * asw; }
@@ -837,14 +943,15 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
             win.proc[a] = !S.mask[st];
             n_unproc += S.mask[st] != 0;
         }
-    if (n_unproc != Aw && S.tau_4D == LFBM5D_DCT) S.tau_4D = LFBM5D_SADCT;
+    if (force_sadct >= 0) S.tau_4D = (force_sadct && p->tau_4D == LFBM5D_DCT) ? (unsigned) LFBM5D_SADCT : p->tau_4D;
+    else if (n_unproc != Aw && S.tau_4D == LFBM5D_DCT) S.tau_4D = LFBM5D_SADCT;
     if (S.tau_4D != S.tables_tau4) {
         pc.tau_4D = S.tau_4D;
         for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); if (setup_tables(T->local[l], step, p, S.tau_4D)) return 1; }
         S.tables_tau4 = S.tau_4D;
     }
     TMARK(0);
-    for (int l = 0; l < nl; l++) {      // padded working set on the rows the own groups touch; running estimate on them as well
+    for (int l = 0; l < nl; l++) {      // padded working set on the rows the own groups touch; running estimate on the own rows
         lfbm5d_ctx *ctx = T->local[l];
         const Band &bd = T->bands[T->local_rank[l]];
         CK(cudaSetDevice(ctx->device));
@@ -853,40 +960,32 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
                    ctx->num.as<float>(), ctx->den.as<float>(), ctx->nsym.as<float>(), ctx->bsym.as<float>(), ctx->numsym.as<float>(),
                    ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) W, (int) H, (int) C, (int) pc.n, bd.y0, bd.c1 - bd.y0, bd.y1);
     }
-    const unsigned max_unproc = n_unproc;
-    unsigned calls = 0;
-    while (n_unproc) {
-        unsigned pst_asw = 0;
-        if (n_unproc == max_unproc && win.mask[cst_asw]) pst_asw = cst_asw;
-        else {      // bm5d.cpp:318-333
-            std::vector<int> items;
-            for (unsigned a = 0; a < Aw; a++) if (win.proc[a] == 0) items.push_back((int) a);
-            std::vector<unsigned long long> hz;
-            if (team_count_zero(T, items, true, pc, hz)) return 1;
-            long long best = -1;
-            for (size_t i = 0; i < items.size(); i++) {
-                const long long z = (long long) (int) hz[i];
-                if (z >= best) { pst_asw = (unsigned) items[i]; best = z; }
-            }
-        }
-        if (calls > 0)      // the running estimate of the window after the previous core call (core:169 / :937), own rows
-            for (int l = 0; l < nl; l++) {
-                lfbm5d_ctx *ctx = T->local[l];
-                const Band &bd = T->bands[T->local_rank[l]];
-                CK(cudaSetDevice(ctx->device));
-                if (bd.y1 > bd.y0)
-                    LAUNCH(ctx, k_est0_rows, grid_for(ctx, (size_t) Aw * (bd.y1 - bd.y0) * pc.wb), 256, 0, step == 1 ? ctx->nsym.as<float>() : ctx->bsym.as<float>(),
-                           ctx->numsym.as<float>(), ctx->densym.as<float>(), ctx->est0.as<float>(), win, (int) pc.wb, (int) pc.hb, (int) C, bd.y0, bd.y1 - bd.y0);
-            }
-        TMARK(1);
-        if (team_est0_exchange(T, pc, win)) return 1;
+    wf.n_unproc = wf.max_unproc = n_unproc;
+    wf.calls = 0;
+    wf.open = n_unproc > 0;
+    if (!wf.open) return 0;
+    return team_window_prepass(T);
+}
+
+int team_window_finish(lfbm5d_team *T, lfbm5d_team *sched_to)
+{
+    StepState &S = T->ss;
+    const lfbm5d_params *p = &S.p;
+    const int nl = (int) T->local.size();
+    PassCfg &pc = S.pc;
+    const unsigned asize = S.asize();
+    const unsigned C = p->chnls, W = p->width, H = p->height;
+    auto &wf = T->wf;
+    LfWindow &win = wf.win;
+    const unsigned Aw = (unsigned) win.A;
+    while (wf.open) {
         unsigned long long cnt = 0;
-        if (team_pass(T, pc, win, (int) pst_asw, (int) cst_asw, &cnt)) return 1;
-        if (T->timing && calls == 0)
+        if (team_pass_finish(T, pc, &cnt)) return 1;
+        if (T->timing && wf.calls == 0)
             for (int i = 0; i < 2; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, T->tev[i], T->tev[i + 1]) == cudaSuccess) T->phase_ms[i] += ms; }
-        calls++;
-        win.proc[pst_asw] += 1;
-        S.proc[win.st[pst_asw]] += 1;
+        wf.calls++;
+        win.proc[wf.pst_asw] += 1;
+        S.proc[win.st[wf.pst_asw]] += 1;
         for (int l = 0; l < nl; l++) {      // crop the accumulators back: the own band and the replica rows shared with the next rank
             lfbm5d_ctx *ctx = T->local[l];
             const Band &bd = T->bands[T->local_rank[l]];
@@ -903,19 +1002,29 @@ int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
         if (pct >= 100.0f)
             for (unsigned a = 0; a < Aw; a++)
                 if (win.proc[a] == 0) { win.proc[a] += 1; S.proc[win.st[a]] += 1; }
-        n_unproc = 0;
-        for (unsigned a = 0; a < Aw; a++) n_unproc += win.proc[a] == 0;
+        wf.n_unproc = 0;
+        for (unsigned a = 0; a < Aw; a++) wf.n_unproc += win.proc[a] == 0;
+        if (!wf.n_unproc) { wf.open = false; break; }
+        if (team_window_prepass(T)) return 1;
     }
     for (int l = 0; l < nl; l++) {
-        lfbm5d_ctx *ctx = T->local[l];
-        ctx->sched.push_back((unsigned) win.st[cst_asw]); ctx->sched.push_back((unsigned) min_s);
-        ctx->sched.push_back((unsigned) min_t); ctx->sched.push_back(calls);
+        lfbm5d_ctx *ctx = sched_to->local[l];
+        ctx->sched.push_back((unsigned) win.st[wf.cst_asw]); ctx->sched.push_back((unsigned) wf.min_s);
+        ctx->sched.push_back((unsigned) wf.min_t); ctx->sched.push_back(wf.calls);
     }
     for (unsigned a = 0; a < Aw; a++) if (win.mask[a]) S.touched[win.st[a]] = 1;
     S.remaining = 0;
     for (unsigned st = 0; st < asize; st++) S.remaining += S.proc[st] == 0;
     S.passes++;
+    // lanes: the unpadding kernels of the window must be through before another lane (or the final estimate) reads num / den
+    if (sched_to != T || !T->lanes.empty())
+        for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); CK(cudaStreamSynchronize(T->local[l]->stream)); }
     return 0;
+}
+
+int team_window(lfbm5d_team *T, unsigned ps, unsigned pt)
+{
+    return team_window_begin(T, ps, pt, -1) || team_window_finish(T, T);
 }
 
 // Final estimate on the rows each rank holds; gather != 0: the bands of `out` are then exchanged so that every rank has all of it
@@ -1031,6 +1140,8 @@ int lfbm5d_team_create_nccl(lfbm5d_team **out, lfbm5d_ctx *ctx, int rank, int wo
 void lfbm5d_team_destroy(lfbm5d_team *T)
 {
     if (!T) return;
+    for (auto Tl : T->lanes) lfbm5d_team_destroy(Tl);
+    T->lanes.clear();
     for (auto c : T->local) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
     if (T->comm && T->peer_ready) {      // nobody frees its buffers while they are mapped elsewhere
         team_peer_close(T);
@@ -1041,12 +1152,42 @@ void lfbm5d_team_destroy(lfbm5d_team *T)
     }
     T->xsegs.release(); T->xflags.release(); T->xdone.release(); T->xflagptrs.release();
     for (auto c : T->local) team_bufs_release(c);
-    if (T->comm) g_nccl.CommDestroy(T->comm);
+    if (T->comm && !T->is_lane) g_nccl.CommDestroy(T->comm);
     if (T->owns_ctx) for (auto c : T->local) lfbm5d_destroy(c);
     delete T;
 }
 
 int lfbm5d_team_local_ranks(lfbm5d_team *T) { return T ? (int) T->local.size() : 0; }
+
+/* Number of lanes of the team (>= 1): independent windows of a step (same level of the static plan) run concurrently, one per lane.
+ * Every further lane has its own contexts (pass buffers: ~22 GB per lane at 17x17x1024^2) and exchange state. */
+int lfbm5d_team_set_lanes(lfbm5d_team *T, int nlanes)
+{
+    if (!T || nlanes < 1 || nlanes > 8 || T->is_lane) return fail("bad lane count (1 .. 8)");
+    while ((int) T->lanes.size() + 1 > nlanes) { lfbm5d_team_destroy(T->lanes.back()); T->lanes.pop_back(); }
+    while ((int) T->lanes.size() + 1 < nlanes) {
+        lfbm5d_team *Tl = new lfbm5d_team();
+        Tl->world = T->world; Tl->owns_ctx = true; Tl->is_lane = true; Tl->comm = T->comm;
+        Tl->use_peer_exchange = T->use_peer_exchange; Tl->peer_ok = T->peer_ok;
+        for (size_t l = 0; l < T->local.size(); l++) {
+            lfbm5d_ctx *c = nullptr;
+            if (lfbm5d_create(&c, T->local[l]->device)) { lfbm5d_team_destroy(Tl); return 1; }
+            Tl->local.push_back(c); Tl->local_rank.push_back(T->local_rank[l]);
+        }
+        T->lanes.push_back(Tl);
+    }
+    return 0;
+}
+
+/* kernels launched by all contexts of the team (all lanes) since the last lfbm5d_reset_stats of each */
+unsigned long long lfbm5d_team_launches(lfbm5d_team *T)
+{
+    if (!T) return 0;
+    unsigned long long n = 0;
+    for (auto c : T->local) n += c->stats.kernel_launches;
+    for (auto Tl : T->lanes) for (auto c : Tl->local) n += c->stats.kernel_launches;
+    return n;
+}
 
 /* one LFBM5D step of ONE light field on the whole team; d_* are arrays of lfbm5d_team_local_ranks() device pointers (one copy of the
  * light field per local rank, [asize][chnls][height][width] floats) */
@@ -1057,10 +1198,38 @@ int lfbm5d_team_step(lfbm5d_team *T, int step, const lfbm5d_params *p, float *co
     if (step != 1 && step != 2) return fail("step must be 1 or 2");
     if (team_step_begin(T, step, p, d_noisy_io, d_basic_io, sai_mask)) return 1;
     const unsigned max_passes = T->local[0]->max_passes;
-    while (T->ss.remaining) {
-        unsigned ps = 0, pt = 0;
-        if (team_select(T, ps, pt) || team_window(T, ps, pt)) return 1;
-        if (max_passes && T->ss.passes >= max_passes) break;
+    if (T->lanes.empty()) {
+        while (T->ss.remaining) {
+            unsigned ps = 0, pt = 0;
+            if (team_select(T, ps, pt) || team_window(T, ps, pt)) return 1;
+            if (max_passes && T->ss.passes >= max_passes) break;
+        }
+    } else {
+        // Several lanes: the windows of a step form a static plan (lfbm5d_step_plan); the windows of one plan level share no SAI and
+        // commute, so they run concurrently, one per lane — the latency-bound parts of a pass (the strip chains of the summed-area
+        // planes, the exchanges, the host's counter read) of one window hide behind the bandwidth-bound parts of the others.
+        const unsigned asize = p->awidth * p->aheight;
+        std::vector<unsigned> plan((size_t) (asize + 1) * 6);
+        const unsigned nwin = lfbm5d_step_plan(p, sai_mask, plan.data(), asize + 1);
+        std::vector<lfbm5d_team *> L;
+        L.push_back(T);
+        for (lfbm5d_team *Tl : T->lanes) L.push_back(Tl);
+        unsigned done = 0, maxlevel = 0;
+        for (unsigned i = 0; i < nwin; i++) maxlevel = std::max(maxlevel, plan[6 * i + 4]);
+        for (unsigned lev = 0; lev <= maxlevel && !(max_passes && done >= max_passes); lev++) {
+            std::vector<unsigned> ws;
+            for (unsigned i = 0; i < nwin; i++) if (plan[6 * i + 4] == lev) ws.push_back(i);
+            for (size_t c0 = 0; c0 < ws.size(); c0 += L.size()) {
+                const size_t c1 = std::min(ws.size(), c0 + L.size());
+                for (size_t j = c0; j < c1; j++) {
+                    const unsigned *e = &plan[6 * ws[j]];
+                    if (team_window_begin(L[j - c0], e[0], e[1], (int) e[5])) return 1;
+                }
+                for (size_t j = c0; j < c1; j++) if (team_window_finish(L[j - c0], T)) return 1;
+                done += (unsigned) (c1 - c0);
+                if (max_passes && done >= max_passes) break;
+            }
+        }
     }
     return team_step_end(T, d_out, gather);
 }
@@ -1123,9 +1292,12 @@ int lfbm5d_sync(lfbm5d_ctx *ctx)
 void lfbm5d_team_stats(lfbm5d_team *T, unsigned long long *bytes_exchanged, unsigned *passes_redone, unsigned long long *tie_patches, int *peer_view)
 {
     if (!T) return;
-    if (bytes_exchanged) *bytes_exchanged = T->bytes_exchanged;
-    if (passes_redone) *passes_redone = T->passes_redone;
-    if (tie_patches) *tie_patches = T->tie_patches;
+    unsigned long long b = T->bytes_exchanged, tp = T->tie_patches;
+    unsigned pr = T->passes_redone;
+    for (auto Tl : T->lanes) { b += Tl->bytes_exchanged; tp += Tl->tie_patches; pr += Tl->passes_redone; }
+    if (bytes_exchanged) *bytes_exchanged = b;
+    if (passes_redone) *passes_redone = pr;
+    if (tie_patches) *tie_patches = tp;
     if (peer_view) *peer_view = T->peer_ready ? 1 : 0;
 }
 
@@ -1147,9 +1319,15 @@ void lfbm5d_team_disable_peer_view(lfbm5d_team *T)
     if (!T) return;
     if (T->comm) team_peer_close(T);
     T->peer_ready = false; T->peer_ok = false;
+    for (auto Tl : T->lanes) lfbm5d_team_disable_peer_view(Tl);
 }
 
 /* 0: exchanges of an NCCL team go through NCCL send / recv even when the buffers are peer-mapped (comparison runs) */
-void lfbm5d_team_use_peer_exchange(lfbm5d_team *T, int on) { if (T) T->use_peer_exchange = on != 0; }
+void lfbm5d_team_use_peer_exchange(lfbm5d_team *T, int on)
+{
+    if (!T) return;
+    T->use_peer_exchange = on != 0;
+    for (auto Tl : T->lanes) Tl->use_peer_exchange = on != 0;
+}
 
 } // extern "C"

@@ -325,14 +325,16 @@ __global__ void __launch_bounds__(256) k_peer_copy(const PeerSegD *__restrict__ 
     }
 }
 
-__global__ void k_peer_wait(const unsigned *flags, int me, int G, unsigned epoch)
+__global__ void k_peer_wait(const unsigned *flags, int me, int G, unsigned epoch, unsigned *timed_out)
 {
     const int q = threadIdx.x;
     if (q < G && q != me) {
         unsigned v;
+        const long long t0 = clock64();
         for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flags + q) : "memory");
             if ((int) (v - epoch) >= 0) break;
+            if (clock64() - t0 > 20000000000ll) { *timed_out = 1u; break; }      // ~10 s: a lost peer must not hang the device (the step then fails)
             __nanosleep(100);
         }
     }

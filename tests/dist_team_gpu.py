@@ -6,6 +6,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # lanes: concurrent streams must not share a hardware queue
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,6 +37,9 @@ def main():
     p1 = L.make_params(10.0, 2.7, aw, ah, 1, W, H, 3, 8, 18, 6, 16, 4, L.ID, L.DCT if not big else L.SADCT, L.HAAR)
     p2 = L.make_params(10.0, 0.0, aw, ah, 1, W, H, 3, 16, 18, 6, 8, 4, L.DCT, L.DCT if not big else L.SADCT, L.HAAR)
     team = D.make_team(eng, dist, dev)
+    lanes = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--lanes=")]
+    if lanes and lanes[0] > 1:
+        team.set_lanes(lanes[0])
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     times = {}
     work, basic, out = noisy.clone(), torch.zeros_like(noisy), torch.zeros_like(noisy)
@@ -71,7 +76,7 @@ def main():
                           "speedup": float(tt[1] / tt[0]) if check else None, "denoised_identical": bool(flags[0]), "noisy_roundtrip_identical": bool(flags[1]),
                           "band_rank0": band, "bytes_sent_rank0": st["bytes_exchanged"], "passes_redone": st["passes_redone"],
                           "tie_patches_rank0": st["tie_patches"], "peer_view": st["peer_view"],
-                          "phase_ms_rank0": phases}), flush=True)
+                          "phase_ms_rank0": phases, "lanes": lanes[0] if lanes else 1}), flush=True)
     team.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flags.min()) == 1 else 1)

@@ -19,8 +19,10 @@ def run_single(L, eng, torch, noisy, mask, p1, p2):
     return w, b, o, s1
 
 
-def run_team(L, torch, world, noisy, mask, p1, p2, gather, peer_view=True):
+def run_team(L, torch, world, noisy, mask, p1, p2, gather, peer_view=True, lanes=1):
     team = L.Team.emulated(0, world)
+    if lanes > 1:
+        team.set_lanes(lanes)
     if not peer_view:
         team.disable_peer_view()
     ws = [noisy.clone() for _ in range(world)]
@@ -92,3 +94,29 @@ def test_team_exact_distance_ties(oracle):
         assert (st["tie_patches"] > 0 and st["passes_redone"] == 0) if peer_view else st["passes_redone"] > 0
         for g in range(3):
             assert torch.equal(outs[g], o0) and torch.equal(ws[g], w0)
+
+
+@pytest.mark.parametrize("world,lanes", [(2, 2), (3, 3), (1, 4)])
+def test_team_lanes_run_independent_windows_concurrently(world, lanes, oracle):
+    """Several lanes: the windows of one level of the static plan (no shared SAI) run concurrently, one per lane, in level order
+    instead of the sequential order. A 6 x 5 light field (12 windows, several levels, one empty SAI with the sticky dct -> sadct
+    switch): still bit-identical to the sequential single-context run."""
+    import torch
+    import lfbm5d_b200 as L
+    dev = torch.device("cuda", 0)
+    aw, ah, H, W = 6, 5, 170, 60
+    clean = lfdata.synth_lf(aw, ah, H, W)
+    noisy = torch.from_numpy(oracle.add_noise(clean, 15.0)).to(dev)
+    mask = np.ones(aw * ah, np.uint32)
+    mask[9] = 0
+    p1 = L.make_params(15.0, 2.7, aw, ah, 1, W, H, 3, 8, 18, 6, 16, 4, L.ID, L.DCT, L.HAAR)
+    p2 = L.make_params(15.0, 0.0, aw, ah, 1, W, H, 3, 16, 18, 6, 8, 4, L.DCT, L.DCT, L.HAAR)
+    plan = L.step_plan(p1, mask)
+    assert len(plan) >= 6 and int(plan[:, 4].max()) + 1 < len(plan)          # some level holds more than one window
+    eng = L.LFBM5D(0)
+    w0, b0, o0, s0 = run_single(L, eng, torch, noisy, mask, p1, p2)
+    eng.close()
+    ws, bs, outs, bands1, bands2, st = run_team(L, torch, world, noisy, mask, p1, p2, gather=1, lanes=lanes)
+    for g in range(world):
+        assert torch.equal(outs[g], o0), "denoised differs on rank %d" % g
+        assert torch.equal(ws[g], w0), "noisy round trip differs on rank %d" % g

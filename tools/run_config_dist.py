@@ -13,6 +13,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # team lanes: concurrent streams must not share a hardware queue
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -28,6 +30,7 @@ def main():
     ap.add_argument("config", type=int, choices=(2, 4, 5))
     ap.add_argument("--sigmas", type=str, default="")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=1)
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -37,6 +40,8 @@ def main():
     eng = L.LFBM5D(local)
     stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     team = D.make_team(eng, dist, dev) if world > 1 and args.config != 4 else None
+    if team is not None and args.lanes > 1:
+        team.set_lanes(args.lanes)
     shapes = {2: (15, 15, 434, 625), 4: (17, 17, 1024, 1024), 5: (9, 9, 2048, 2048)}
     aw, ah, H, W = shapes[args.config]
     asize = aw * ah
