@@ -1214,22 +1214,36 @@ int lfbm5d_team_step(lfbm5d_team *T, int step, const lfbm5d_params *p, float *co
         std::vector<lfbm5d_team *> L;
         L.push_back(T);
         for (lfbm5d_team *Tl : T->lanes) L.push_back(Tl);
-        unsigned done = 0, maxlevel = 0;
+        // Software pipeline over the plan sorted by level: window i goes to lane i mod L; before it begins, every earlier window
+        // that shares an SAI with it — and the lane's previous window — is finished (counters read, accumulators written back).
+        // Up to L windows are in flight; only true dependencies stall. Every rank walks the same deterministic sequence.
+        const unsigned asw = 2 * p->an + 1;
+        std::vector<unsigned> order;
+        unsigned maxlevel = 0;
         for (unsigned i = 0; i < nwin; i++) maxlevel = std::max(maxlevel, plan[6 * i + 4]);
-        for (unsigned lev = 0; lev <= maxlevel && !(max_passes && done >= max_passes); lev++) {
-            std::vector<unsigned> ws;
-            for (unsigned i = 0; i < nwin; i++) if (plan[6 * i + 4] == lev) ws.push_back(i);
-            for (size_t c0 = 0; c0 < ws.size(); c0 += L.size()) {
-                const size_t c1 = std::min(ws.size(), c0 + L.size());
-                for (size_t j = c0; j < c1; j++) {
-                    const unsigned *e = &plan[6 * ws[j]];
-                    if (team_window_begin(L[j - c0], e[0], e[1], (int) e[5])) return 1;
-                }
-                for (size_t j = c0; j < c1; j++) if (team_window_finish(L[j - c0], T)) return 1;
-                done += (unsigned) (c1 - c0);
-                if (max_passes && done >= max_passes) break;
-            }
+        for (unsigned lev = 0; lev <= maxlevel; lev++)
+            for (unsigned i = 0; i < nwin; i++) if (plan[6 * i + 4] == lev) order.push_back(i);
+        if (max_passes && order.size() > max_passes) order.resize(max_passes);
+        auto overlap = [&](unsigned a_, unsigned b_) {
+            const unsigned *x = &plan[6 * a_], *y = &plan[6 * b_];
+            return !(x[2] + asw <= y[2] || y[2] + asw <= x[2] || x[3] + asw <= y[3] || y[3] + asw <= x[3]);
+        };
+        const size_t nL = L.size();
+        std::vector<int> state(order.size(), 0);          // 0 not begun, 1 in flight, 2 finished
+        auto finish = [&](size_t q) -> int {
+            if (state[q] != 1) return 0;
+            state[q] = 2;
+            return team_window_finish(L[q % nL], T);
+        };
+        for (size_t q = 0; q < order.size(); q++) {
+            if (q >= nL && finish(q - nL)) return 1;        // the lane's previous window
+            for (size_t d = 0; d < q; d++)
+                if (state[d] == 1 && overlap(order[d], order[q]) && finish(d)) return 1;
+            const unsigned *e = &plan[6 * order[q]];
+            if (team_window_begin(L[q % nL], e[0], e[1], (int) e[5])) return 1;
+            state[q] = 1;
         }
+        for (size_t q = 0; q < order.size(); q++) if (finish(q)) return 1;
     }
     return team_step_end(T, d_out, gather);
 }
