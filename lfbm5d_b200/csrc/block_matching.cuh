@@ -9,6 +9,7 @@
 // The rounding of that recurrence decides ~1 % of the match lists, so it is reproduced operation for operation.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 // ---- geometry shared by all planes of one launch ----
 struct SatGeom {
@@ -43,7 +44,35 @@ struct SatPlane {
 struct SatGroup {
     const float *img1, *img2;
     int oy, oxmin, nplanes, first_plane;
+    int z1, z2;             // plane indices of img1 / img2 in the tensor map of the estimate planes (TMA path)
 };
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier, as used for the source-row rings of k_sat2 ----
+__device__ __forceinline__ void lf_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void lf_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lf_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = (unsigned) __cvta_generic_to_shared(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+// one box of the 3-D tensor (x, y, plane) into shared memory; elements outside the tensor arrive as zeros
+__device__ __forceinline__ void lf_tma_load_3d(float *smem_dst, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"((unsigned) __cvta_generic_to_shared(smem_dst)), "l"(map), "r"((unsigned) __cvta_generic_to_shared(bar)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
 
 template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 {
@@ -61,11 +90,16 @@ template <int IMM> __device__ __forceinline__ float lf_lds(unsigned addr)
 // has always started before its consumer (no deadlock). Source rows of both images are staged once per CTA with cp.async
 // into two 128(+K)-row shared-memory rings (row stride 64 floats: the skewed reads are bank-conflict free) and reused by all
 // planes of the group; squared differences are formed on the fly.
-template <bool SELF, int K>
+// TMA: the source rows arrive as 8-row x 64-column boxes of the estimate planes (cp.async.bulk.tensor, one elected thread, an
+// mbarrier per CTA; out-of-image elements are zero-filled by the hardware) instead of 4-byte cp.async copies issued by every thread;
+// needs a 16-byte multiple as the row pitch of the planes (the host picks the variant).
+template <bool SELF, int K, bool TMA>
 __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGroup *__restrict__ groups, const SatPlane *__restrict__ planes,
-                                                          int ngroups, unsigned long long *bnd, int *ticket_counter)
+                                                          int ngroups, unsigned long long *bnd, int *ticket_counter,
+                                                          const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ float s_dyn[];
+    extern __shared__ __align__(128) float s_dyn[];
+    __shared__ __align__(8) unsigned long long s_mbar;
     // source-row rings of img1 / img2: 128 rows + K mirror rows (slot s < K is also stored at s + 128, so that the
     // row K below any slot is always at slot + K without wrapping)
     float *R1 = s_dyn, *R2 = s_dyn + (128 + K) * 64;
@@ -89,6 +123,9 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     const int lastlane = min(31, W - 1 - (strip << 5));
     const bool has_next = strip + 1 < g.nstrips;
     const int xb1 = c0 - 1, xb2 = c0 - 1 + G.oxmin;
+    // TMA boxes start at a 16-byte multiple of the row (an unaligned innermost coordinate faults, tools/probe/tma_probe.cu): the
+    // box starts up to three columns early and the lanes read at that shift; img2 needs 32 + 13 + K <= 61 columns, so 64 still do
+    const int xs1 = TMA ? (xb1 & 3) : 0, xs2 = TMA ? (xb2 & 3) : 0;
     const int oxo = PA.ox - G.oxmin;                   // column shift of plane A inside the img2 ring (plane B: +1)
     const int ymax = min(g.row_end - 1 + k - 1, h - 1);
     const size_t pstride = (size_t) g.pstrips * h;
@@ -98,20 +135,43 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     const size_t bB = hasB ? pstride : 0;              // offset from plane A's boundary column to plane B's
     const unsigned tag_hi = g.epoch << 16;
 
+    // ring slot of source row y of img1 (and of row y + oy of img2): counted from row lo + k, so that the 32-row loads of the
+    // chunks start at multiples of 32 (no box straddles the end of the ring)
+    const int rbase = lo + k;
+    unsigned mbar_parity = 0;
     auto load_rows = [&](int y0, int y1) {
+        if (TMA) {
+            if (y0 > ymax) return;
+            if (tid == 0) {
+                const int nbox = (y1 - y0 + 1) >> 3;
+                int nmir = 0;
+                for (int b = 0; b < nbox; ++b) nmir += (((y0 + 8 * b - rbase) & 127) < K) ? 1 : 0;
+                lf_mbar_expect_tx(&s_mbar, (unsigned) (2 * (nbox + nmir)) * 8u * 64u * 4u);
+                for (int b = 0; b < nbox; ++b) {
+                    const int y = y0 + 8 * b, sl = (y - rbase) & 127;
+                    lf_tma_load_3d(R1 + sl * 64, &tmap, &s_mbar, xb1 - xs1, y, G.z1);
+                    lf_tma_load_3d(R2 + sl * 64, &tmap, &s_mbar, xb2 - xs2, y + G.oy, G.z2);
+                    if (sl < K) {
+                        lf_tma_load_3d(R1 + (sl + 128) * 64, &tmap, &s_mbar, xb1 - xs1, y, G.z1);
+                        lf_tma_load_3d(R2 + (sl + 128) * 64, &tmap, &s_mbar, xb2 - xs2, y + G.oy, G.z2);
+                    }
+                }
+            }
+            return;
+        }
         if (y1 > ymax) y1 = ymax;
         const int n = (y1 - y0 + 1) * 128;
         for (int t = tid; t < n; t += blockDim.x) {
             const int y = y0 + (t >> 7), c = t & 63, which = (t >> 6) & 1;
             if (which == 0) {
-                const int x = xb1 + c, sl = y & 127;
+                const int x = xb1 + c, sl = (y - rbase) & 127;
                 float *dst = &R1[sl * 64 + c];
                 if (x < w) {
                     lf_cp_async4(dst, G.img1 + (size_t) y * w + x);
                     if (sl < K) lf_cp_async4(dst + 128 * 64, G.img1 + (size_t) y * w + x);
                 } else { *dst = 0.f; if (sl < K) dst[128 * 64] = 0.f; }
             } else {
-                const int yy = y + G.oy, x = xb2 + c, sl = yy & 127;
+                const int yy = y + G.oy, x = xb2 + c, sl = (y - rbase) & 127;
                 float *dst = &R2[sl * 64 + c];
                 if (yy >= 0 && yy < h && x >= 0 && x < w) {
                     lf_cp_async4(dst, G.img2 + (size_t) yy * w + x);
@@ -154,9 +214,15 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
             if (hasB) outB[o] = vB;
         }
     };
+    // rows the loads of a chunk wait for: cp.async groups of the thread, or the transaction count of the CTA's mbarrier
+    auto rows_wait = [&](int y0) {
+        if (TMA) { if (y0 <= ymax) { lf_mbar_wait(&s_mbar, mbar_parity); mbar_parity ^= 1u; } }
+        else lf_cp_async_wait_all();
+    };
     // ---- prologue: source rows of chunk 0; the first row of the sums comes from k_sat_edges ----
+    if (TMA) { if (tid == 0) lf_mbar_init(&s_mbar, 1); __syncthreads(); }
     load_rows(lo, lo + 32 + k - 1);
-    lf_cp_async_wait_all();
+    rows_wait(lo);
     __syncthreads();
 
     float curv[2] = { 0.f, 0.f }, prevv[2] = { 0.f, 0.f };
@@ -172,10 +238,10 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
     // i+K-1 is K ring rows further (mirror rows: no wrap). Both advance by one ring row (256 B) per step.
     const int nsteps = (Hh - 1) + 31;
     const int nchunks = (nsteps + 31) >> 5;
-    const unsigned sb1 = (unsigned) __cvta_generic_to_shared(R1) + 4u * (unsigned) lane;
-    const unsigned sb2 = (unsigned) __cvta_generic_to_shared(R2) + 4u * (unsigned) (lane + oxo);
-    unsigned ro1 = (unsigned) (((lo + 1 - lane - 1) & 127) * 256);
-    unsigned ro2 = (unsigned) (((lo + 1 - lane - 1 + G.oy) & 127) * 256);
+    const unsigned sb1 = (unsigned) __cvta_generic_to_shared(R1) + 4u * (unsigned) (lane + xs1);
+    const unsigned sb2 = (unsigned) __cvta_generic_to_shared(R2) + 4u * (unsigned) (lane + oxo + xs2);
+    unsigned ro1 = (unsigned) (((lo + 1 - lane - 1 - rbase) & 127) * 256);
+    unsigned ro2 = ro1;      // both rings are indexed by the img1 row
     const bool colz = SELF && (j + k - 1 >= g.xlim);
     // lane 0 of strip 0 owns the first column of the plane: its sums come from k_sat_edges (through the same per-chunk staging the
     // other strips use for the last column of their predecessor) and replace what the general recurrence would give
@@ -300,7 +366,7 @@ __global__ void __launch_bounds__(SAT_NW * 32, 3) k_sat2(SatGeom g, const SatGro
                 __syncwarp();
             }
         }
-        lf_cp_async_wait_all();
+        rows_wait(lo + 32 * (q + 1) + k);
         __syncthreads();
     }
 }

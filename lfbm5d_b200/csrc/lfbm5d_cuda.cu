@@ -185,6 +185,9 @@ struct lfbm5d_ctx {
     lfbm5d_stats stats{};
     bool timing = false;
     unsigned sat_epoch = 0;        // pass counter (16 bits): tags the strip hand-off words of k_sat2
+    CUtensorMap tmap_est0;         // TMA view of the running-estimate planes [A][h_b][w_b] (source rows of k_sat2)
+    size_t tmap_key[4] = { 0, 0, 0, 0 };
+    bool tmap_ok = false;
     bool bm_only = false;          // lfbm5d_debug_block_matching: a pass stops behind the match tables
     cudaEvent_t ev[5]{};
     unsigned max_passes = 0;
@@ -498,6 +501,7 @@ SatPlan *sat_plan(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int p
         for (int djx0 = 0; djx0 < Ns; djx0 += 2 * SAT_NW) {
             SatGroup G{};
             G.img1 = ref0; G.img2 = ref0; G.oy = di; G.oxmin = djx0 - (int) pc.nSim;      // core:3331: dk = di*w + djx - nSim
+            G.z1 = G.z2 = pst;
             G.first_plane = (int) P.planes.size();
             for (int djx = djx0; djx < std::min(Ns, djx0 + 2 * SAT_NW); djx++) {
                 SatPlane Q{};
@@ -529,6 +533,7 @@ SatPlan *sat_plan(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int p
         for (int di = 0; di < Nd; di++) {      // core:3516: dk = (di - nDisp)*w + (dj - nDisp)
             SatGroup G{};
             G.img1 = ref0; G.img2 = est0 + (size_t) st * pg.plane; G.oy = di - (int) pc.nDisp; G.oxmin = -(int) pc.nDisp;
+            G.z1 = pst; G.z2 = st;
             G.first_plane = (int) P.planes.size();
             for (int dj = 0; dj < Nd; dj++) {
                 SatPlane Q{};
@@ -561,6 +566,34 @@ SatPlan *sat_plan(lfbm5d_ctx *ctx, const PassCfg &pc, const LfWindow &win, int p
     return ctx->sat_cache.back().get();
 }
 
+// Tensor map of the estimate planes for the TMA loads of k_sat2 (cuTensorMapEncodeTiled through the runtime's driver entry point:
+// no link-time dependency on libcuda). Needs a row pitch that is a multiple of 16 bytes; otherwise the cp.async variant runs.
+int ensure_tmap(lfbm5d_ctx *ctx, const PassCfg &pc)
+{
+    const size_t key[4] = { (size_t) ctx->est0.p, pc.wb, pc.hb, pc.A };
+    if (memcmp(key, ctx->tmap_key, sizeof(key)) == 0) return 0;
+    memcpy(ctx->tmap_key, key, sizeof(key));
+    ctx->tmap_ok = false;
+    memset(&ctx->tmap_est0, 0, sizeof(ctx->tmap_est0));
+    if (((size_t) pc.wb * 4) % 16 != 0 || ((size_t) ctx->est0.p % 16) != 0 || getenv("LFBM5D_NO_TMA")) return 0;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn enc = nullptr;
+    if (!enc) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp) { cudaGetLastError(); return 0; }
+        enc = (encode_fn) fp;
+    }
+    const cuuint64_t dims[3] = { pc.wb, pc.hb, pc.A };
+    const cuuint64_t strides[2] = { (cuuint64_t) pc.wb * 4, (cuuint64_t) pc.wb * pc.hb * 4 };
+    const cuuint32_t box[3] = { 64, 8, 1 }, estr[3] = { 1, 1, 1 };
+    if (enc(&ctx->tmap_est0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ctx->est0.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return 0;
+    ctx->tmap_ok = true;
+    return 0;
+}
+
 // New pass: reset the two ticket counters and move on to the next epoch of the hand-off tags (1 .. 65535; when the counter wraps the
 // words are cleared, so that a word written 65535 passes ago under another geometry can never be taken for a fresh one)
 int next_sat_epoch(lfbm5d_ctx *ctx)
@@ -591,7 +624,8 @@ int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg
     g.negzero2 = 0x8000000080000000ull;
     g.frow = ctx->frow.as<float>(); g.fcol = ctx->fcol.as<float>();
     const size_t smem = 2 * (128 + pc.k) * 64 * 4;
-    auto kfn = pc.k == 8 ? k_sat2<true, 8> : k_sat2<true, 16>;
+    if (ensure_tmap(ctx, pc)) return 1;
+    auto kfn = ctx->tmap_ok ? (pc.k == 8 ? k_sat2<true, 8, true> : k_sat2<true, 16, true>) : (pc.k == 8 ? k_sat2<true, 8, false> : k_sat2<true, 16, false>);
     auto kedge = pc.k == 8 ? k_sat_edges<true, 8> : k_sat_edges<true, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const size_t smem_e = sate_smem((int) pc.k);
@@ -599,7 +633,7 @@ int launch_sat_self(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int sg
     kedge<<<dim3(sg1 - sg0, 2), SATE_NT, smem_e, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), ctx->frow.as<float>(), ctx->fcol.as<float>());
     ctx->stats.kernel_launches++;
     kfn<<<(sg1 - sg0) * P.self_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + sg0, P.d_planes.as<SatPlane>(), sg1 - sg0,
-                                                                  ctx->bnd.as<unsigned long long>(), ticket);
+                                                                  ctx->bnd.as<unsigned long long>(), ticket, ctx->tmap_est0);
     ctx->stats.kernel_launches++;
     return 0;
 }
@@ -616,7 +650,8 @@ int launch_sat_stereo(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int 
     g.frow = ctx->frow.as<float>(); g.fcol = ctx->fcol.as<float>();
     const size_t smem = 2 * (128 + pc.k) * 64 * 4;
     const int ngroups = (s1 - s0) * P.groups_per_slot;
-    auto kfn = pc.k == 8 ? k_sat2<false, 8> : k_sat2<false, 16>;
+    if (ensure_tmap(ctx, pc)) return 1;
+    auto kfn = ctx->tmap_ok ? (pc.k == 8 ? k_sat2<false, 8, true> : k_sat2<false, 16, true>) : (pc.k == 8 ? k_sat2<false, 8, false> : k_sat2<false, 16, false>);
     auto kedge = pc.k == 8 ? k_sat_edges<false, 8> : k_sat_edges<false, 16>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const size_t smem_e = sate_smem((int) pc.k);
@@ -625,7 +660,7 @@ int launch_sat_stereo(lfbm5d_ctx *ctx, const PassCfg &pc, const SatPlan &P, int 
                                                        ctx->frow.as<float>(), ctx->fcol.as<float>());
     ctx->stats.kernel_launches++;
     kfn<<<ngroups * P.st_strips, SAT_NW * 32, smem, strm>>>(g, P.d_groups.as<SatGroup>() + P.nself_groups + s0 * P.groups_per_slot,
-                                                            P.d_planes.as<SatPlane>(), ngroups, ctx->bnd.as<unsigned long long>(), ticket + 1);
+                                                            P.d_planes.as<SatPlane>(), ngroups, ctx->bnd.as<unsigned long long>(), ticket + 1, ctx->tmap_est0);
     ctx->stats.kernel_launches++;
     return 0;
 }

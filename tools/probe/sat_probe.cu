@@ -3,12 +3,13 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -I lfbm5d_b200/csrc -o gpurun_out/sat_probe tools/probe/sat_probe.cu
 #include "block_matching.cuh"
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include <algorithm>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
 
-template <bool SELF, int K>
+template <bool SELF, int K, bool TMA = true>
 int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
 {
     const int n = nSim + nDisp;
@@ -33,7 +34,7 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
         for (int slot = 0; slot < nslots_or_groups; slot++)
             for (int di = 0; di < Nd; di++) {
                 SatGroup G{};
-                G.img1 = img; G.img2 = img + (size_t) (1 + slot % 8) * plane; G.oy = di - nDisp; G.oxmin = -nDisp; G.first_plane = (int) planes.size();
+                G.img1 = img; G.img2 = img + (size_t) (1 + slot % 8) * plane; G.z1 = 0; G.z2 = 1 + slot % 8; G.oy = di - nDisp; G.oxmin = -nDisp; G.first_plane = (int) planes.size();
                 for (int dj = 0; dj < Nd; dj++) { SatPlane P{}; P.ox = dj - nDisp; P.out_skew = sums + ((size_t) slot * Nd * Nd + di * Nd + dj) * stride; planes.push_back(P); G.nplanes++; }
                 groups.push_back(G);
             }
@@ -55,7 +56,7 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
         for (int di = 0; di <= nSim && ng < nslots_or_groups; di++)
             for (int djx0 = 0; djx0 < Ns && ng < nslots_or_groups; djx0 += 2 * SAT_NW, ng++) {
                 SatGroup G{};
-                G.img1 = img; G.img2 = img; G.oy = di; G.oxmin = djx0 - nSim; G.first_plane = (int) planes.size();
+                G.img1 = img; G.img2 = img; G.z1 = G.z2 = 0; G.oy = di; G.oxmin = djx0 - nSim; G.first_plane = (int) planes.size();
                 for (int djx = djx0; djx < std::min(Ns, djx0 + 2 * SAT_NW); djx++) {
                     SatPlane P{}; const int ddk = di * Ns + djx;
                     P.ox = djx - nSim; P.out_at = s_at + (size_t) ddk * R; P.out_mir = s_mir + (size_t) ddk * R; P.mir_di = di; P.mir_dc = nSim - djx;
@@ -80,7 +81,21 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
     CK(cudaMalloc(&frow, planes.size() * (size_t) w * 4)); CK(cudaMalloc(&fcol, planes.size() * (size_t) h * 4));
     g.frow = frow; g.fcol = fcol;
     const size_t smem = 2 * (128 + K) * 64 * 4;
-    auto kfn = k_sat2<SELF, K>;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool tma = TMA && (w % 4 == 0);
+    if (tma) {
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
+        const cuuint64_t dims[3] = { (cuuint64_t) w, (cuuint64_t) h, 9 }, strides[2] = { (cuuint64_t) w * 4, (cuuint64_t) w * h * 4 };
+        const cuuint32_t box[3] = { 64, 8, 1 }, estr[3] = { 1, 1, 1 };
+        if (((encode_fn) fp)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("tensor map failed\n"); return 1; }
+    }
+    auto kfn = tma ? k_sat2<SELF, K, true> : k_sat2<SELF, K, false>;
     CK(cudaFuncSetAttribute((const void *) kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
@@ -96,7 +111,7 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
         }
         CK(cudaEventRecord(e2));
         g.epoch = (unsigned) (r + 1);
-        kfn<<<(int) groups.size() * g.nstrips, SAT_NW * 32, smem>>>(g, dg, dp, (int) groups.size(), bnd, prog);
+        kfn<<<(int) groups.size() * g.nstrips, SAT_NW * 32, smem>>>(g, dg, dp, (int) groups.size(), bnd, prog, tmap);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaGetLastError());
@@ -105,7 +120,7 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
         cudaEventElapsedTime(&ms, e0, e2);
         best_edge = std::min(best_edge, ms);
     }
-    printf("%s K=%d groups=%zu planes=%zu strips=%d CTAs=%zu : %.3f ms (edges %.3f)  (%.2f us per plane)\n", SELF ? "self  " : "stereo", K, groups.size(), planes.size(), g.nstrips,
+    printf("%s%s K=%d groups=%zu planes=%zu strips=%d CTAs=%zu : %.3f ms (edges %.3f)  (%.2f us per plane)\n", SELF ? "self  " : "stereo", tma ? " tma" : " cpa", K, groups.size(), planes.size(), g.nstrips,
            groups.size() * g.nstrips, best, best_edge, 1e3 * best / planes.size());
     cudaFree(frow); cudaFree(fcol);
     cudaFree(img); cudaFree(sums); cudaFree(s_at); cudaFree(s_mir); cudaFree(rowmap); cudaFree(colmap); cudaFree(dp); cudaFree(dg); cudaFree(bnd); cudaFree(prog);
@@ -114,6 +129,8 @@ int run(int w, int h, int nDisp, int nSim, int nslots_or_groups, int reps)
 
 int main(int argc, char **argv)
 {
+    if (argc > 1 && argv[1][0] == 't') return run<true, 16>(1072, 1072, 6, 18, 1, 1);      // one self group through the TMA variant
+    if (argc > 1 && argv[1][0] == 'u') return run<false, 8>(1072, 1072, 6, 18, 1, 1);      // one stereo slot through the TMA variant
     if (argc > 1 && argv[1][0] == 'o') return run<true, 16>(1072, 1072, 6, 18, 1, 1);      // one launch (for ncu)
     if (argc > 1 && argv[1][0] == 'f') return run<true, 16>(1072, 1072, 6, 18, 57, 1);     // full self launch (for ncu)
     if (argc > 1) {      // lone strips: unit time and per-strip lag
@@ -123,6 +140,8 @@ int main(int argc, char **argv)
         for (int hh : { 272, 528 }) if (run<true, 16>(1072, hh, 6, 18, 1, 3)) return 1;
         return 0;
     }
+    for (int s : { 1, 8 }) if (run<false, 16, false>(1072, 1072, 6, 18, s, 3)) return 1;
+    for (int gq : { 1, 7, 57 }) if (run<true, 16, false>(1072, 1072, 6, 18, gq, 3)) return 1;
     for (int s : { 1, 2, 4, 8 }) if (run<false, 16>(1072, 1072, 6, 18, s, 3)) return 1;
     for (int s : { 1, 2, 4, 8 }) if (run<false, 8>(1072, 1072, 6, 18, s, 3)) return 1;
     for (int gq : { 1, 4, 7, 13, 26, 57 }) if (run<true, 16>(1072, 1072, 6, 18, gq, 3)) return 1;
