@@ -134,7 +134,9 @@ unsigned long long lfbm5d_team_launches(lfbm5d_team *team);   /* kernels launche
 /* One step (1 or 2) of ONE light field on the whole team. d_*: arrays of lfbm5d_team_local_ranks() device pointers, one replica of the
  * light field per local rank ([asize][chnls][height][width] floats, as for lfbm5d_step{1,2}_device). A rank reads and colour-transforms
  * only the rows of its band (+ halo) of d_noisy_io / d_basic_io; on return d_out[l] holds the rows [row_lo, keep_hi) of lfbm5d_team_band
- * (d_basic_io of step 2 may be the d_out of step 1 as it is), or, with gather != 0, the complete result on every rank. */
+ * (d_basic_io of step 2 may be the d_out of step 1 as it is: when the bands of step 2 read rows a rank did not keep from step 1 —
+ * other patch size / step, another number of ranks with rows — the team first sends the step-1 bands around), or, with gather != 0,
+ * the complete result on every rank. */
 int  lfbm5d_team_step(lfbm5d_team *team, int step, const lfbm5d_params *p, float *const *d_noisy_io, float *const *d_basic_io,
                       const unsigned *sai_mask, float *const *d_out, int gather);
 int  lfbm5d_team_band(lfbm5d_team *team, int rank, int *row_lo, int *row_hi, int *keep_hi);

@@ -86,6 +86,7 @@ struct lfbm5d_team {
     // step state shared by all ranks (every rank takes the same decisions from the same exchanged counts)
     StepState ss;
     std::vector<Band> bands;
+    std::vector<Band> held;                // bands of a step 1 that ended without a gather: rank g holds the rows [i0, j1) of LF_basic
     std::vector<float *> d_noisy, d_basic; // per local rank
     unsigned long long bytes_exchanged = 0;
     unsigned passes_redone = 0;
@@ -705,6 +706,7 @@ int team_peer_setup(lfbm5d_team *T, const PassCfg &pc, int step)
         // gather buffers of team_step_end
         size_t maxrows = 0;
         for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (T->bands[g].i1 - T->bands[g].i0));
+        for (const Band &hb : T->held) maxrows = std::max<size_t>(maxrows, (size_t) (hb.i1 - hb.i0));      // step 1 of this team: already allocated
         const size_t blk = (size_t) T->ss.asize() * pc.C * maxrows * pc.W * 4;
         TeamCtxBufs *b = team_bufs(ctx);
         if (!T->is_lane && (b->gsend.ensure(blk) || b->grecv.ensure(blk * G))) return 1;
@@ -773,6 +775,48 @@ int team_peer_setup(lfbm5d_team *T, const PassCfg &pc, int step)
     return 0;
 }
 
+// The interior rows [i0, i1) of every rank's band of the light field d_lf (one pointer per local rank), sent to every other rank:
+// afterwards every rank holds all rows. Staged through the gather buffers (packed rows of all planes).
+int team_gather_bands(lfbm5d_team *T, const std::vector<Band> &bands, float *const *d_lf)
+{
+    StepState &S = T->ss;
+    const lfbm5d_params *p = &S.p;
+    const int nl = (int) T->local.size(), G = T->world;
+    const int W = (int) p->width, H = (int) p->height;
+    const size_t nplanes = (size_t) S.asize() * p->chnls;
+    size_t maxrows = 0;
+    for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (bands[g].i1 - bands[g].i0));
+    const size_t blk = nplanes * maxrows * W * 4;
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        const Band &bd = bands[T->local_rank[l]];
+        TeamCtxBufs *b = team_bufs(ctx);
+        CK(cudaSetDevice(ctx->device));
+        if (b->gsend.ensure(blk) || b->grecv.ensure(blk * G)) return 1;      // sized by team_peer_setup: nothing grows here
+        if (bd.i1 > bd.i0)
+            LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_lf[l], b->gsend.as<float>(), nplanes, W, H, bd.i0, bd.i1 - bd.i0, 0);
+    }
+    std::vector<TeamSeg> segs;
+    for (int g = 0; g < G; g++) {
+        const Band &bd = bands[g];
+        for (int h = 0; h < G; h++)
+            if (h != g) segs.push_back({ g, h, TB_GSEND, TB_GRECV, 0, (size_t) g * blk, nplanes * (size_t) (bd.i1 - bd.i0) * W * 4 });
+    }
+    if (team_exchange(T, segs)) return 1;
+    for (int l = 0; l < nl; l++) {
+        lfbm5d_ctx *ctx = T->local[l];
+        TeamCtxBufs *b = team_bufs(ctx);
+        CK(cudaSetDevice(ctx->device));
+        for (int g = 0; g < G; g++) {
+            const Band &bd = bands[g];
+            if (g == T->local_rank[l] || bd.i1 <= bd.i0) continue;
+            LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_lf[l], b->grecv.as<float>() + (size_t) g * (blk / 4), nplanes, W, H,
+                   bd.i0, bd.i1 - bd.i0, 1);
+        }
+    }
+    return 0;
+}
+
 int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *const *d_noisy, float *const *d_basic, const unsigned *mask_)
 {
     if (validate(p_, step)) return 1;
@@ -796,6 +840,16 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
     S.touched.assign(asize, 0);
     S.passes = 0;
     T->bands = team_bands(S.pc, T->world);
+    // Step 1 of this team left LF_basic band-resident (no gather) and the bands of this step read rows some rank does not hold (other
+    // patch size / step: other bands, possibly another number of ranks with rows): the owners send their rows around first. Every
+    // rank takes the same decision from the same two band tables. (Config 3: the step-2 bands lie inside the step-1 bands, nothing moves.)
+    bool late_gather = false;
+    if (step == 2 && (int) T->held.size() == T->world)
+        for (int g = 0; g < T->world; g++) {
+            const Band &nb = T->bands[g], &hb = T->held[g];
+            if (nb.j1 > nb.j0 && (nb.j0 < hb.i0 || nb.j1 > hb.j1)) late_gather = true;
+        }
+    if (step == 1 || !late_gather) T->held.clear();
     T->d_noisy.assign(d_noisy, d_noisy + nl);
     T->d_basic.assign(nl, nullptr);
     if (step == 2) T->d_basic.assign(d_basic, d_basic + nl);
@@ -810,7 +864,7 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
         if (S.docolor && bd.j1 > bd.j0) {      // only the rows this rank's groups read (own band + the rows it shares with the next rank)
             LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * p->width), 256, 0, T->d_noisy[l], ctx->mask.as<unsigned>(), asize,
                    (int) p->width, (int) p->height, p->color_space, 1, bd.j0, bd.j1 - bd.j0);
-            if (step == 2)
+            if (step == 2 && !late_gather)
                 LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * p->width), 256, 0, T->d_basic[l], ctx->mask.as<unsigned>(), asize,
                        (int) p->width, (int) p->height, p->color_space, 1, bd.j0, bd.j1 - bd.j0);
         }
@@ -818,6 +872,18 @@ int team_step_begin(lfbm5d_team *T, int step, const lfbm5d_params *p_, float *co
         CK(cudaMemsetAsync(ctx->den.p, 0, asize * each * 4, ctx->stream));
     }
     if (team_peer_setup(T, S.pc, step)) return 1;       // allocates the pass buffers (under the export protocol of NCCL teams)
+    if (late_gather) {
+        if (team_gather_bands(T, T->held, T->d_basic.data())) return 1;
+        T->held.clear();
+        for (int l = 0; l < nl; l++) {
+            lfbm5d_ctx *ctx = T->local[l];
+            const Band &bd = T->bands[T->local_rank[l]];
+            CK(cudaSetDevice(ctx->device));
+            if (S.docolor && bd.j1 > bd.j0)
+                LAUNCH(ctx, k_color_rows, grid_for(ctx, (size_t) asize * (bd.j1 - bd.j0) * p->width), 256, 0, T->d_basic[l], ctx->mask.as<unsigned>(), asize,
+                       (int) p->width, (int) p->height, p->color_space, 1, bd.j0, bd.j1 - bd.j0);
+        }
+    }
     for (int l = 0; l < nl; l++) {
         lfbm5d_ctx *ctx = T->local[l];
         CK(cudaSetDevice(ctx->device));
@@ -1055,39 +1121,10 @@ int team_step_end(lfbm5d_team *T, float *const *d_out, int gather)
         }
         CK(cudaGetLastError());
     }
-    if (gather && G > 1) {
-        const size_t nplanes = (size_t) asize * C;
-        size_t maxrows = 0;
-        for (int g = 0; g < G; g++) maxrows = std::max<size_t>(maxrows, (size_t) (T->bands[g].i1 - T->bands[g].i0));
-        const size_t blk = nplanes * maxrows * W * 4;
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            const Band &bd = T->bands[T->local_rank[l]];
-            TeamCtxBufs *b = team_bufs(ctx);
-            CK(cudaSetDevice(ctx->device));
-            if (b->gsend.ensure(blk) || b->grecv.ensure(blk * G)) return 1;
-            if (bd.i1 > bd.i0)
-                LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_out[l], b->gsend.as<float>(), nplanes, W, H, bd.i0, bd.i1 - bd.i0, 0);
-        }
-        std::vector<TeamSeg> segs;
-        for (int g = 0; g < G; g++) {
-            const Band &bd = T->bands[g];
-            for (int h = 0; h < G; h++)
-                if (h != g) segs.push_back({ g, h, TB_GSEND, TB_GRECV, 0, (size_t) g * blk, nplanes * (size_t) (bd.i1 - bd.i0) * W * 4 });
-        }
-        if (team_exchange(T, segs)) return 1;
-        for (int l = 0; l < nl; l++) {
-            lfbm5d_ctx *ctx = T->local[l];
-            TeamCtxBufs *b = team_bufs(ctx);
-            CK(cudaSetDevice(ctx->device));
-            for (int g = 0; g < G; g++) {
-                const Band &bd = T->bands[g];
-                if (g == T->local_rank[l] || bd.i1 <= bd.i0) continue;
-                LAUNCH(ctx, k_pack_rows, grid_for(ctx, nplanes * (bd.i1 - bd.i0) * W), 256, 0, d_out[l], b->grecv.as<float>() + (size_t) g * (blk / 4), nplanes, W, H,
-                       bd.i0, bd.i1 - bd.i0, 1);
-            }
-        }
-    }
+    if (gather && G > 1 && team_gather_bands(T, T->bands, d_out)) return 1;
+    // no gather: step 2 on this team finds the rows of LF_basic where this step left them (team_step_begin)
+    T->held.clear();
+    if (!gather && G > 1 && S.step == 1) T->held = T->bands;
     for (int l = 0; l < nl; l++) { CK(cudaSetDevice(T->local[l]->device)); CK(cudaStreamSynchronize(T->local[l]->stream)); }
     S.active = false;
     return 0;

@@ -120,3 +120,41 @@ def test_team_lanes_run_independent_windows_concurrently(world, lanes, oracle):
     for g in range(world):
         assert torch.equal(outs[g], o0), "denoised differs on rank %d" % g
         assert torch.equal(ws[g], w0), "noisy round trip differs on rank %d" % g
+
+
+@pytest.mark.parametrize("world,params", [(4, "config2"), (8, "config2"), (4, "config3")])
+def test_team_band_resident_basic_with_other_step2_bands(world, params, oracle):
+    """Step 1 without a gather (LF_basic stays band-resident), then step 2 on the same team, with more ranks than row bands: the
+    two steps cut different bands (other patch size / step, another number of ranks that get rows at all), so step 2 reads rows of
+    LF_basic a rank did not keep. The team has to send the step-1 bands around first (team_step_begin). BASELINE config-2 parameters
+    (`1 18 3 16 3 bior / 8 18 3 8 3 dct`) and the README parameters, twice on the same team object; bit-identical to one context."""
+    import torch
+    import lfbm5d_b200 as L
+    dev = torch.device("cuda", 0)
+    aw, ah, H, W = 4, 3, 217, 157
+    clean = lfdata.synth_lf(aw, ah, H, W)
+    noisy = torch.from_numpy(oracle.add_noise(clean, 10.0)).to(dev)
+    mask = np.ones(aw * ah, np.uint32)
+    if params == "config2":
+        p1 = L.make_params(10.0, 2.7, aw, ah, 1, W, H, 3, 1, 18, 3, 16, 3, L.BIOR, L.SADCT, L.HAAR)
+        p2 = L.make_params(10.0, 0.0, aw, ah, 1, W, H, 3, 8, 18, 3, 8, 3, L.DCT, L.SADCT, L.HAAR)
+    else:
+        p1 = L.make_params(10.0, 2.7, aw, ah, 1, W, H, 3, 8, 18, 6, 16, 4, L.ID, L.SADCT, L.HAAR)
+        p2 = L.make_params(10.0, 0.0, aw, ah, 1, W, H, 3, 16, 18, 6, 8, 4, L.DCT, L.SADCT, L.HAAR)
+    b1 = [L.plan_band(world, g, 1, p1) for g in range(world)]
+    b2 = [L.plan_band(world, g, 2, p2) for g in range(world)]
+    assert any(b2[g][2] > b2[g][0] and (b2[g][0] < b1[g][0] or b2[g][2] > b1[g][2]) for g in range(world)), "bands nest: the case is not exercised"
+    eng = L.LFBM5D(0)
+    w0, b0, o0, s0 = run_single(L, eng, torch, noisy, mask, p1, p2)
+    eng.close()
+    team = L.Team.emulated(0, world)
+    for rep in range(2):
+        ws = [noisy.clone() for _ in range(world)]
+        bs = [torch.zeros_like(noisy) for _ in range(world)]
+        outs = [torch.zeros_like(noisy) for _ in range(world)]
+        team.step(1, p1, [t.data_ptr() for t in ws], None, mask, [t.data_ptr() for t in bs], gather=0)
+        team.step(2, p2, [t.data_ptr() for t in ws], [t.data_ptr() for t in bs], mask, [t.data_ptr() for t in outs], gather=1)
+        torch.cuda.synchronize()
+        for g in range(world):
+            assert torch.equal(outs[g], o0), "denoised differs on rank %d (repetition %d)" % (g, rep)
+    team.close()

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--sigmas", type=str, default="")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=1)
+    ap.add_argument("--no-peer", action="store_true", help="team exchanges through NCCL send / recv instead of the peer-memory kernels")
+    ap.add_argument("--check", action="store_true", help="compare the team's result with the single-GPU run on every rank (bit for bit)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -42,6 +44,8 @@ def main():
     team = D.make_team(eng, dist, dev) if world > 1 and args.config != 4 else None
     if team is not None and args.lanes > 1:
         team.set_lanes(args.lanes)
+    if team is not None and args.no_peer:
+        team.use_peer_exchange(False)
     shapes = {2: (15, 15, 434, 625), 4: (17, 17, 1024, 1024), 5: (9, 9, 2048, 2048)}
     aw, ah, H, W = shapes[args.config]
     asize = aw * ah
@@ -119,6 +123,19 @@ def main():
                     "windows_step2": int(len(sched)), "core_calls_step2": int(sched[:, 3].sum()) if len(sched) else 0}
             if team is not None:
                 info["team"] = team.stats()
+                info["team"]["peer_exchange"] = not args.no_peer
+            if team is not None and args.check:
+                res = out.clone()
+                with torch.cuda.stream(stream):
+                    work.copy_(noisy, non_blocking=True)
+                eng.step1_device(p1, work.data_ptr(), mask, basic.data_ptr())
+                eng.step2_device(p2, work.data_ptr(), basic.data_ptr(), mask, out.data_ptr())
+                torch.cuda.synchronize()
+                same = torch.tensor([int(torch.equal(res, out))], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                info["identical_to_single_gpu"] = bool(int(same.item()))
+                info["max_abs_diff_rank0"] = float((res - out).abs().max())
+                info["psnr_single_gpu"] = float(10.0 * torch.log10(255.0 ** 2 / torch.mean((out - clean) ** 2)))
         if rank == 0:
             info.update({"n_gpus": world, "lf": [ah, aw, H, W], "sigma": sigma, "ms": ms, "lf_mpix_per_s": asize * H * W / (ms * 1e-3) / 1e6,
                          "psnr_noisy": float(10.0 * torch.log10(255.0 ** 2 / torch.mean((noisy - clean) ** 2))), "psnr_denoised": psnr})
