@@ -16,6 +16,19 @@ void lfio_add_noise(const float *img, float *out, size_t n, float sigma, unsigne
 /* compute_psnr (utilities.cpp:412-435): float accumulator, psnr = 20 log10(255 / rmse) */
 void lfio_psnr(const float *a, const float *b, size_t n, float *psnr, float *rmse);
 
+
+/* PNG files as the command lines read and write them (io_png.c:116-260 read_png_f32: channels of the file, 16 -> 8 bits, 1/2/4-bit
+ * samples unpacked, any interlace; io_png.c:560-700 write_png_f32: 8 bits, floor(x + .5) clamped). Planar floats c*W*H + i*W + j.
+ * lfio_png_read with out == NULL only reports the size. Return 0 on success, 1 on error. */
+int lfio_png_read(const char *name, float *out, size_t capacity, size_t *w, size_t *h, size_t *c);
+int lfio_png_write(const char *name, const float *data, size_t w, size_t h, size_t c);
+/* compute_psnr_LF (utilities_LF.cpp:639-700), compute_diff_LF (:702-745) and write_psnr_LF (:782-869) on light fields stored as
+ * [asize][each] floats; stats4 = (avg psnr, std psnr, avg rmse, std rmse). The report is appended to file_name. */
+int lfio_psnr_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float *psnr, float *rmse, float *stats4);
+int lfio_diff_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float sigma, float *diff);
+int lfio_write_psnr_LF(const char *file_name, const char *LF_name, const unsigned *mask, unsigned ang_major, unsigned awidth, unsigned aheight,
+                       const float *psnr, float avg_psnr, float std_psnr, const float *rmse, float avg_rmse, float std_rmse);
+
 #ifdef __cplusplus
 }
 #endif

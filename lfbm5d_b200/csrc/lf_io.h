@@ -1,4 +1,4 @@
-// Host glue of the command-line drivers: a self-contained 8/16-bit PNG codec over
+// Host glue of the command-line drivers: a self-contained PNG codec (all bit depths, Adam7) over
 // zlib (the reference wraps libpng, io_png.c:379 / :700; libpng is not in this image), the light-field loader / saver
 // with the reference's file naming (utilities_LF.cpp:105-112), noise (utilities.cpp:154-185, mt19937ar), PSNR / RMSE
 // (utilities.cpp:412-435, utilities_LF.cpp:639-700), difference images (utilities.cpp:440-470) and the PSNR report
@@ -26,7 +26,44 @@ namespace lfio {
 inline uint32_t be32(const unsigned char *p) { return ((uint32_t) p[0] << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3]; }
 inline int paeth(int a, int b, int c) { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
 
-// Reads a PNG into planar float (c*W*H + i*W + j), dropping alpha like read_png_f32 (io_png.c:379). Returns false on error.
+// One pass of a PNG image (the whole image, or one of the seven Adam7 sub-images): pw x ph pixels of `bits` bits, every scanline
+// preceded by its filter type; unfiltered in place (PNG specification section 9: the filters work on bytes, `fb` = bytes per complete
+// pixel, at least 1) and unpacked to one byte per sample at (x0 + x * dx, y0 + y * dy) of the full image. Returns the bytes consumed.
+inline size_t png_pass(unsigned char *raw, size_t avail, size_t pw, size_t ph, unsigned nch, unsigned depth, std::vector<unsigned char> &img, size_t w,
+                       size_t x0, size_t y0, size_t dx, size_t dy, bool *ok)
+{
+    if (!pw || !ph) return 0;
+    const size_t bits = (size_t) nch * depth, rowbytes = (pw * bits + 7) / 8, fb = bits >= 8 ? bits / 8 : 1;
+    if (avail < (rowbytes + 1) * ph) { *ok = false; return 0; }
+    for (size_t y = 0; y < ph; y++) {
+        unsigned char *line = raw + y * (rowbytes + 1) + 1;
+        const unsigned char ft = line[-1], *up = y ? line - (rowbytes + 1) : nullptr;
+        if (ft > 4) { *ok = false; return 0; }
+        for (size_t x = 0; x < rowbytes; x++) {
+            const int a = x >= fb ? line[x - fb] : 0, b = up ? up[x] : 0, cc = (up && x >= fb) ? up[x - fb] : 0;
+            int v = line[x];
+            switch (ft) { case 1: v += a; break; case 2: v += b; break; case 3: v += (a + b) / 2; break; case 4: v += paeth(a, b, cc); break; default: break; }
+            line[x] = (unsigned char) v;
+        }
+        unsigned char *dst = &img[((y0 + y * dy) * w + x0) * nch];
+        for (size_t x = 0; x < pw; x++, dst += dx * nch)
+            for (unsigned ch = 0; ch < nch; ch++) {
+                const size_t sidx = x * nch + ch;
+                if (depth == 8) dst[ch] = line[sidx];
+                else if (depth == 16) dst[ch] = line[2 * sidx];      // most significant byte, as PNG_TRANSFORM_STRIP_16 does
+                else {      // 1, 2, 4 bits, leftmost sample in the high-order bits; unpacked, not scaled (PNG_TRANSFORM_PACKING)
+                    const size_t bit = sidx * depth;
+                    dst[ch] = (unsigned char) ((line[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1));
+                }
+            }
+    }
+    return (rowbytes + 1) * ph;
+}
+
+// Reads a PNG into planar float (c*W*H + i*W + j) the way read_png_f32 does (io_png.c:379 -> :116-260: png_read_png with
+// PNG_TRANSFORM_STRIP_16 | PNG_TRANSFORM_PACKING and nothing else): c = the channels of the file (1 gray or palette INDEX, 2
+// gray + alpha, 3 RGB, 4 RGBA; load_LF then keeps 3 of 4), 16-bit samples cut to their high byte, 1/2/4-bit samples unpacked
+// without scaling, any interlace method (Adam7 sub-images are put back in place). Returns false on error.
 inline bool read_png_f32(const std::string &name, std::vector<float> &out, size_t &w, size_t &h, size_t &c)
 {
     std::ifstream f(name.c_str(), std::ios::binary);
@@ -36,50 +73,48 @@ inline bool read_png_f32(const std::string &name, std::vector<float> &out, size_
     if (buf.size() < 33 || memcmp(buf.data(), sig, 8) != 0) return false;
     size_t pos = 8;
     unsigned depth = 0, ctype = 0, interlace = 0;
-    std::vector<unsigned char> idat, plte;
+    std::vector<unsigned char> idat;
+    w = h = 0;
     while (pos + 12 <= buf.size()) {
         const uint32_t len = be32(&buf[pos]);
         const std::string type((const char *) &buf[pos + 4], 4);
-        if (pos + 12 + len > buf.size()) return false;
+        if (pos + 12 + (size_t) len > buf.size()) return false;
         const unsigned char *d = &buf[pos + 8];
-        if (type == "IHDR") { w = be32(d); h = be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
-        else if (type == "PLTE") plte.assign(d, d + len);
+        if (type == "IHDR") { if (len < 13) return false; w = be32(d); h = be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
         else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
         else if (type == "IEND") break;
-        pos += 12 + len;
+        pos += 12 + (size_t) len;
     }
-    if (!w || !h || (depth != 8 && depth != 16) || interlace != 0) return false;     // Adam7 not supported
     const unsigned nch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-    if (!nch || (ctype == 3 && depth != 8)) return false;
-    const size_t bpp = nch * depth / 8, stride = w * bpp;
-    std::vector<unsigned char> raw((stride + 1) * h);
-    uLongf rawlen = raw.size();
-    if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK || rawlen != raw.size()) return false;
-    std::vector<unsigned char> img(stride * h);
-    for (size_t y = 0; y < h; y++) {
-        const unsigned char ft = raw[y * (stride + 1)], *src = &raw[y * (stride + 1) + 1];
-        unsigned char *dst = &img[y * stride];
-        const unsigned char *up = y ? &img[(y - 1) * stride] : nullptr;
-        for (size_t x = 0; x < stride; x++) {
-            const int a = x >= bpp ? dst[x - bpp] : 0, b = up ? up[x] : 0, cc = (up && x >= bpp) ? up[x - bpp] : 0;
-            int v = src[x];
-            switch (ft) { case 1: v += a; break; case 2: v += b; break; case 3: v += (a + b) / 2; break; case 4: v += paeth(a, b, cc); break; default: break; }
-            dst[x] = (unsigned char) v;
-        }
+    const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                        : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8) : (depth == 8 || depth == 16);
+    if (!w || !h || !nch || !depth_ok || interlace > 1 || w > (1u << 20) || h > (1u << 20)) return false;
+    // Adam7: start / step of the seven passes (PNG specification section 8.2); pass 0 of a non-interlaced file is the image
+    static const unsigned ax0[7] = { 0, 4, 0, 2, 0, 1, 0 }, ay0[7] = { 0, 0, 4, 0, 2, 0, 1 }, adx[7] = { 8, 8, 4, 4, 2, 2, 1 }, ady[7] = { 8, 8, 8, 4, 4, 2, 2 };
+    const size_t bits = (size_t) nch * depth;
+    size_t rawlen = 0;
+    const int npass = interlace ? 7 : 1;
+    for (int q = 0; q < npass; q++) {
+        const size_t pw = interlace ? (w + adx[q] - 1 - ax0[q]) / adx[q] : w, ph = interlace ? (h + ady[q] - 1 - ay0[q]) / ady[q] : h;
+        if (pw && ph) rawlen += ((pw * bits + 7) / 8 + 1) * ph;
     }
-    const bool color = ctype == 2 || ctype == 6 || ctype == 3;
-    c = color ? 3 : 1;
+    std::vector<unsigned char> raw(rawlen);
+    uLongf got = (uLongf) rawlen;
+    if (idat.empty() || uncompress(raw.data(), &got, idat.data(), (uLong) idat.size()) != Z_OK || got != rawlen) return false;
+    std::vector<unsigned char> img(w * h * nch);
+    bool ok = true;
+    size_t off = 0;
+    for (int q = 0; q < npass && ok; q++) {
+        const size_t pw = interlace ? (w + adx[q] - 1 - ax0[q]) / adx[q] : w, ph = interlace ? (h + ady[q] - 1 - ay0[q]) / ady[q] : h;
+        off += png_pass(raw.data() + off, rawlen - off, pw, ph, nch, depth, img, w, interlace ? ax0[q] : 0, interlace ? ay0[q] : 0,
+                        interlace ? adx[q] : 1, interlace ? ady[q] : 1, &ok);
+    }
+    if (!ok) return false;
+    c = nch;
     out.assign(w * h * c, 0.0f);
-    for (size_t y = 0; y < h; y++)
-        for (size_t x = 0; x < w; x++) {
-            const unsigned char *px = &img[y * stride + x * bpp];
-            for (size_t ch = 0; ch < c; ch++) {
-                float v;
-                if (ctype == 3) v = 3 * px[0] + ch < plte.size() ? plte[3 * px[0] + ch] : 0;
-                else v = depth == 8 ? px[ch] : px[2 * ch];      // 16 bit: most significant byte, as png_set_strip_16 does
-                out[ch * w * h + y * w + x] = v;
-            }
-        }
+    for (size_t ch = 0; ch < c; ch++)
+        for (size_t y = 0; y < h; y++)
+            for (size_t x = 0; x < w; x++) out[ch * w * h + y * w + x] = (float) img[(y * w + x) * nch + ch];
     return true;
 }
 
@@ -155,8 +190,8 @@ inline int load_LF(const char *dir, const char *sub, const char *sep, std::vecto
             LF[st].assign(tmp.begin(), tmp.begin() + w * h * c);
             for (size_t k = 0; k < w * h * c; k++) if (tmp[k]) { mask[st] = 1; break; }      // utilities_LF.cpp:149-154
         }
-    std::cout << std::endl << " Light field size :" << std::endl << " - angular size   = " << awidth << " x " << aheight << std::endl
-              << " - spatial size   = " << *width << " x " << *height << std::endl << " - nb of channels = " << *chnls << std::endl;
+    std::cout << std::endl << " Light field size :" << std::endl << " - awidth         = " << awidth << std::endl << " - aheight        = " << aheight << std::endl
+              << " - width          = " << *width << std::endl << " - height         = " << *height << std::endl << " - nb of channels = " << *chnls << std::endl;
     return EXIT_SUCCESS;
 }
 inline int save_LF(const char *dir, const char *sub, const char *sep, const std::vector<std::vector<float> > &LF, const std::vector<unsigned> &mask,

@@ -141,4 +141,54 @@ void lfio_psnr(const float *a, const float *b, size_t n, float *psnr, float *rms
     *psnr = 20.0f * log10f(255.0f / (*rmse));
 }
 
+// ---- the file formats and the report of the command lines, for callers / tests without a C++ toolchain ----
+int lfio_png_read(const char *name, float *out, size_t capacity, size_t *w, size_t *h, size_t *c)
+{
+    std::vector<float> v;
+    size_t ww = 0, hh = 0, cc = 0;
+    if (!name || !w || !h || !c || !lfio::read_png_f32(name, v, ww, hh, cc)) return 1;
+    *w = ww; *h = hh; *c = cc;
+    if (out) { if (capacity < v.size()) return 1; memcpy(out, v.data(), v.size() * sizeof(float)); }
+    return 0;
+}
+
+int lfio_png_write(const char *name, const float *data, size_t w, size_t h, size_t c)
+{
+    return name && data && lfio::write_png_f32(name, data, w, h, c) ? 0 : 1;
+}
+
+static std::vector<std::vector<float> > lf_of(const float *a, unsigned asize, size_t each)
+{
+    std::vector<std::vector<float> > v(asize);
+    for (unsigned st = 0; st < asize; st++) v[st].assign(a + (size_t) st * each, a + (size_t) (st + 1) * each);
+    return v;
+}
+
+int lfio_psnr_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float *psnr, float *rmse, float *stats4)
+{
+    const std::vector<unsigned> m(mask, mask + asize);
+    std::vector<float> ps, rm;
+    if (lfio::compute_psnr_LF(lf_of(lf1, asize, each), lf_of(lf2, asize, each), m, ps, &stats4[0], &stats4[1], rm, &stats4[2], &stats4[3]) != EXIT_SUCCESS) return 1;
+    memcpy(psnr, ps.data(), asize * sizeof(float));
+    memcpy(rmse, rm.data(), asize * sizeof(float));
+    return 0;
+}
+
+int lfio_diff_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float sigma, float *diff)
+{
+    const std::vector<unsigned> m(mask, mask + asize);
+    std::vector<std::vector<float> > d;
+    lfio::compute_diff_LF(lf_of(lf1, asize, each), lf_of(lf2, asize, each), m, d, sigma);
+    for (unsigned st = 0; st < asize; st++) if (m[st]) memcpy(diff + (size_t) st * each, d[st].data(), each * sizeof(float));
+    return 0;
+}
+
+int lfio_write_psnr_LF(const char *file_name, const char *LF_name, const unsigned *mask, unsigned ang_major, unsigned awidth, unsigned aheight,
+                       const float *psnr, float avg_psnr, float std_psnr, const float *rmse, float avg_rmse, float std_rmse)
+{
+    const unsigned asize = awidth * aheight;
+    return lfio::write_psnr_LF(file_name, LF_name, std::vector<unsigned>(mask, mask + asize), ang_major, awidth, aheight, std::vector<float>(psnr, psnr + asize),
+                               avg_psnr, std_psnr, std::vector<float>(rmse, rmse + asize), avg_rmse, std_rmse, LFBM5D_ROWMAJOR) == EXIT_SUCCESS ? 0 : 1;
+}
+
 } // extern "C"

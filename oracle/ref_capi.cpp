@@ -369,4 +369,33 @@ int ref_compute_psnr(const float *a, const float *b, size_t n, float *psnr, floa
     return compute_psnr(x, y, psnr, rmse);
 }
 
+/* compute_psnr_LF / compute_diff_LF / write_psnr_LF (utilities_LF.cpp:639-700, :702-745, :782-869) on [asize][each] arrays */
+int ref_compute_psnr_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float *psnr, float *rmse, float *stats4)
+{
+    CoutSilencer quiet;
+    vector<unsigned> m(mask, mask + asize);
+    vector<float> ps, rm;
+    const int rc = compute_psnr_LF(to_vv(lf1, asize, each), to_vv(lf2, asize, each), m, ps, &stats4[0], &stats4[1], rm, &stats4[2], &stats4[3]);
+    if (rc == EXIT_SUCCESS) { memcpy(psnr, ps.data(), asize * sizeof(float)); memcpy(rmse, rm.data(), asize * sizeof(float)); }
+    return rc;
+}
+int ref_compute_diff_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float sigma, float *diff)
+{
+    CoutSilencer quiet;
+    vector<unsigned> m(mask, mask + asize);
+    vector<vector<float> > d;
+    const int rc = compute_diff_LF(to_vv(lf1, asize, each), to_vv(lf2, asize, each), m, d, sigma);
+    if (rc == EXIT_SUCCESS) from_vv(d, diff, each);
+    return rc;
+}
+int ref_write_psnr_LF(const char *file_name, const char *LF_name, const unsigned *mask, unsigned ang_major, unsigned awidth, unsigned aheight,
+                      const float *psnr, float avg_psnr, float std_psnr, const float *rmse, float avg_rmse, float std_rmse)
+{
+    CoutSilencer quiet;
+    const unsigned asize = awidth * aheight;
+    vector<unsigned> m(mask, mask + asize);
+    return write_psnr_LF(file_name, LF_name, m, ang_major, awidth, aheight, vector<float>(psnr, psnr + asize), avg_psnr, std_psnr,
+                         vector<float>(rmse, rmse + asize), avg_rmse, std_rmse);
+}
+
 } // extern "C"

@@ -31,7 +31,7 @@ def test_host_library_exports_and_noise(oracle):
     import lfbm5d_b200 as L
     src = open(os.path.join(ROOT, "include", "lfbm5d_host_c.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    syms = sorted(set(re.findall(r"\b(lfio_[a-z0-9_]+)\s*\(", src)))
+    syms = sorted(set(re.findall(r"\b(lfio_[A-Za-z0-9_]+)\s*\(", src)))
     h = L.load_host_library()
     assert syms == sorted(L.HOST_EXPORTS)
     for s in syms:

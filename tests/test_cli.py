@@ -53,6 +53,34 @@ def test_cli_readme_command(tmp_path):
     assert len(vals) == 3 and vals[0] < vals[1] < vals[2] and vals[2] - vals[0] > 5.0
     den = np.asarray(Image.open(str(tmp_path / "denoisedLF" / "SAI_02_02.png")), dtype=np.float32).transpose(2, 0, 1)
     assert np.sqrt(np.mean((den - clean[4]) ** 2)) < 8.0
+    # The files and the report are exactly what the library's entry points give on the same input, written in the reference's
+    # formats: noise = mt19937ar seeded LFBM5D_SEED + st on the 8-bit source (utilities.cpp:154-185), images rounded floor(x + .5)
+    # and clamped (io_png.c:648-650), PSNR / RMSE of the unrounded floats with the reference's accumulation (utilities.cpp:412-435).
+    import lfbm5d_b200 as L
+    src8 = np.clip(np.floor(clean + 0.5), 0, 255).astype(np.float32)
+    noisy = L.add_noise(src8, 25.0, seed0=20171016)
+    mask = np.ones(9, np.uint32)
+    eng = L.LFBM5D(0)
+    p1 = L.make_params(25.0, 2.7, 3, 3, 1, 72, 64, 3, 8, 18, 6, 16, 4, L.ID, L.SADCT, L.HAAR)
+    p2 = L.make_params(25.0, 0.0, 3, 3, 1, 72, 64, 3, 16, 18, 6, 8, 4, L.DCT, L.SADCT, L.HAAR)
+    basic, n1 = eng.step1(p1, noisy, mask)
+    out, b2, n2 = eng.step2(p2, n1, basic, mask)
+    eng.close()
+
+    def as_png(x):
+        return np.clip(np.floor(x + np.float32(0.5)), 0, 255).astype(np.uint8)
+    for s in range(3):
+        for t in range(3):
+            st = s * 3 + t
+            for d, arr in (("noisyLF", noisy), ("basicLF", basic), ("denoisedLF", out)):      # basic is saved before step 2 round-trips it
+                img = np.asarray(Image.open(str(tmp_path / d / ("SAI_%02d_%02d.png" % (s + 1, t + 1))))).transpose(2, 0, 1)
+                assert np.array_equal(img, as_png(arr[st])), (d, st)
+    blocks = re.findall(r"-> Average PSNR (\w+) = ([0-9.]+)\n-> Standard deviation PSNR \w+ = ([0-9.e+-]+)\nPSNR for all \w+ SAIs:\n((?:[0-9. ]+\n){3})", txt)
+    assert [b[0] for b in blocks] == ["noisy", "basic", "denoised"]
+    for (name, avg, std, rows), arr in zip(blocks, (noisy, basic, out)):
+        want = [L.psnr(src8[st], arr[st])[0] for st in range(9)]
+        got = [float(v) for v in rows.split()]
+        assert np.allclose(got, want, rtol=2e-6, atol=0) and abs(float(avg) - np.mean(want)) < 2e-4, (name, got, want)   # 6 significant digits printed
     # second mode: no ground truth, noisy light field read back from disk (utilities_LF.cpp:1187)
     args2 = list(args)
     args2[1] = "none"

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--sigmas", type=str, default="")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--lanes", type=int, default=1)
+    ap.add_argument("--lf", type=str, default="", help="aw,ah,H,W instead of the configuration's light field (small shapes: more ranks than row bands)")
     ap.add_argument("--no-peer", action="store_true", help="team exchanges through NCCL send / recv instead of the peer-memory kernels")
     ap.add_argument("--check", action="store_true", help="compare the team's result with the single-GPU run on every rank (bit for bit)")
     args = ap.parse_args()
@@ -47,7 +48,7 @@ def main():
     if team is not None and args.no_peer:
         team.use_peer_exchange(False)
     shapes = {2: (15, 15, 434, 625), 4: (17, 17, 1024, 1024), 5: (9, 9, 2048, 2048)}
-    aw, ah, H, W = shapes[args.config]
+    aw, ah, H, W = shapes[args.config] if not args.lf else tuple(int(x) for x in args.lf.split(","))
     asize = aw * ah
     sigmas = [float(s) for s in args.sigmas.split(",")] if args.sigmas else ([10.0, 25.0, 50.0] if args.config == 5 else [10.0])
     clean = torch.empty((asize, 3, H, W), device=dev)
