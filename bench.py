@@ -123,6 +123,14 @@ def algorithmic_flops_bm(which):
     return R * (2 * s["nSim"] + 1) ** 2 * s["k"] ** 2 * 3.0 + 8 * min(P, R * s["N"]) * (2 * s["nDisp"] + 1) ** 2 * s["k"] ** 2 * 3.0
 
 
+def executed_flops_bm(which):
+    """What the summed-area kernels execute per pass: 14 flop per (pixel, offset plane), (nSim+1)(2nSim+1) self and 8 (2nDisp+1)^2 disparity planes."""
+    s = CFG[which]
+    n = s["nSim"] + s["nDisp"]
+    planes = (s["nSim"] + 1) * (2 * s["nSim"] + 1) + 8 * (2 * s["nDisp"] + 1) ** 2
+    return planes * float(CFG["H"] + n) * float(CFG["W"] + n) * 14.0
+
+
 def clean_lf(aw, ah, H, W, C, seed=12345):
     """Deterministic synthetic clean light field: procedural texture cropped at 1 px / view disparity (tests/lfdata.py)."""
     import lfdata
@@ -300,10 +308,16 @@ def run_ours(args):
         fl = (algorithmic_flops_bm("s1"), algorithmic_flops_bm("s2"))
         ach_bm = (fl[0] + fl[1]) / ((sat_ms[0] + sat_ms[1]) * 1e-3) / 1e12
         fp32 = fp32_peak()
-        roof_bm = {"kernel": "k_sat_edges + k_sat2 (summed-area planes of a pass, both streams)", "bound": "fp32", "achieved": ach_bm, "peak": fp32["tflops"],
-                   "unit": "TFLOP/s", "frac": ach_bm / fp32["tflops"], "peak_source": fp32["source"],
-                   "model": "direct-SSD-EQUIVALENT flops (SURVEY 8(d)): what a direct block matching would execute; the kernels run the reference's float32 "
-                            "summed-area recurrence (~15 flop per (pixel, offset)), so this figure is not a pipe utilisation (see profiles/ for the ncu issue / FMA-pipe numbers)",
+        ex = (executed_flops_bm("s1"), executed_flops_bm("s2"))
+        ex_bm = (ex[0] + ex[1]) / ((sat_ms[0] + sat_ms[1]) * 1e-3) / 1e12
+        roof_bm = {"kernel": "k_sat_edges + k_sat2 (summed-area planes of a pass, both streams; source rows by TMA)", "bound": "fp32", "achieved": ex_bm, "peak": fp32["tflops"],
+                   "unit": "TFLOP/s", "frac": ex_bm / fp32["tflops"], "peak_source": fp32["source"],
+                   "model": "EXECUTED flops: 14 per (pixel, offset plane) of the reference's float32 summed-area recurrence (4 differences, 4 squares, 6 additions; "
+                            "703 self + 8 x 169 disparity planes of ~(H + n) x (W + n) sums). The recurrence is issue / latency bound (shared-memory operands, one "
+                            "shuffle and a dependent chain of 6 additions per step), not FMA bound: see the issue and FMA-pipe columns of profiles/*_kernels.md",
+                   "direct_ssd_equivalent": {"tflops": ach_bm, "of_fp32_peak": ach_bm / fp32["tflops"],
+                                             "model": "SURVEY 8(d): the flops a direct block matching (3 per pixel pair) would execute for the same match lists; "
+                                                      "an equivalence, not a pipe utilisation (it exceeds 1 because the summed areas share work between patches)"},
                    "ms_per_pass": {"step1": sat_ms[0], "step2": sat_ms[1]}}
         phases = {"step1_ms_per_pass": {"block_matching": s1.ms_block_matching / n1, "groups": g_ms[0], "aggregate": a_ms[0]},
                   "step2_ms_per_pass": {"block_matching": s2.ms_block_matching / n2, "groups": g_ms[1], "aggregate": a_ms[1]}}

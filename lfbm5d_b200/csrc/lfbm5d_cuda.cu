@@ -1273,24 +1273,6 @@ int download_lf(lfbm5d_ctx *ctx, const DevBuf &buf, float *const *host, const un
     return 0;
 }
 
-// The colour-round-tripped copy of an input light field (the reference's side effect on LF_noisy / LF_basic) does not depend on
-// the passes: compute it right after the upload and send it back on the second stream while the step runs. Nothing to do
-// (the caller's arrays already hold the result) without a colour transform.
-int early_roundtrip(lfbm5d_ctx *ctx, const lfbm5d_params *p, const DevBuf &src, DevBuf &rt, float *const *host, const unsigned *mask,
-                    unsigned asize, size_t each)
-{
-    if (!(p->chnls == 3 && p->color_space != LFBM5D_RGB)) return 0;
-    if (rt.ensure(asize * each * 4) || ctx->mask.ensure(asize * 4)) return 1;
-    CK(cudaMemcpyAsync(ctx->mask.p, mask, asize * 4, cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_roundtrip, grid_for(ctx, asize * (each / 3)), 256, 0, src.as<float>(), rt.as<float>(), ctx->mask.as<unsigned>(), asize, each / 3,
-           p->color_space);
-    CK(cudaEventRecord(ctx->ev_rt, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_rt, 0));
-    for (unsigned st = 0; st < asize; st++)
-        if (mask[st]) CK(cudaMemcpyAsync(host[st], rt.as<float>() + st * each, each * 4, cudaMemcpyDeviceToHost, ctx->stream2));
-    return 0;
-}
-
 } // namespace
 
 extern "C" {

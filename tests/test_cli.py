@@ -80,7 +80,7 @@ def test_cli_readme_command(tmp_path):
     for (name, avg, std, rows), arr in zip(blocks, (noisy, basic, out)):
         want = [L.psnr(src8[st], arr[st])[0] for st in range(9)]
         got = [float(v) for v in rows.split()]
-        assert np.allclose(got, want, rtol=2e-6, atol=0) and abs(float(avg) - np.mean(want)) < 2e-4, (name, got, want)   # 6 significant digits printed
+        assert np.allclose(got, want, rtol=0, atol=1e-4) and abs(float(avg) - np.mean(want)) < 2e-4, (name, got, want)   # 6 significant digits printed
     # second mode: no ground truth, noisy light field read back from disk (utilities_LF.cpp:1187)
     args2 = list(args)
     args2[1] = "none"
