@@ -142,3 +142,28 @@ def test_team_bands_tile_the_light_field():
         p.join(120)
         assert p.exitcode == 0
     assert ret[0] == ret[1] and ret[0][0][0] == 0 and ret[0][0][1] == ret[0][1][0] and ret[0][1][1] == 1024
+
+
+def test_step2_bands_nest_in_step1_bands_or_need_the_late_gather():
+    """LF_basic may stay band-resident between the steps of a team (lfbm5d_team_step, gather = 0): rank g then holds the rows
+    [lo, keep) of its step-1 band. That is enough for step 2 only if its bands lie inside; otherwise team_step_begin sends the step-1
+    bands around first. Host logic of that decision, from the planned bands (no GPU): the README parameters on 1024-row SAIs nest
+    on every world size the bench runs; BASELINE config 2 (434 rows) on 8 ranks does not (step 1 gives rows to 7 ranks, step 2
+    to 8) — the case that produced 11 dB before the fix."""
+    import lfbm5d_b200 as L
+
+    def nests(world, p1, p2):
+        b1 = [L.plan_band(world, r, 1, p1) for r in range(world)]
+        b2 = [L.plan_band(world, r, 2, p2) for r in range(world)]
+        return all(b2[r][2] <= b2[r][0] or (b2[r][0] >= b1[r][0] and b2[r][2] <= b1[r][2]) for r in range(world)), b1, b2
+    p1 = L.make_params(10.0, 2.7, 17, 17, 1, 1024, 1024, 3, 8, 18, 6, 16, 4, L.ID, L.SADCT, L.HAAR)
+    p2 = L.make_params(10.0, 0.0, 17, 17, 1, 1024, 1024, 3, 16, 18, 6, 8, 4, L.DCT, L.SADCT, L.HAAR)
+    for world in (1, 2, 4, 8):
+        ok, b1, b2 = nests(world, p1, p2)
+        assert ok, (world, b1, b2)
+    q1 = L.make_params(10.0, 2.7, 15, 15, 1, 625, 434, 3, 1, 18, 3, 16, 3, L.BIOR, L.SADCT, L.HAAR)
+    q2 = L.make_params(10.0, 0.0, 15, 15, 1, 625, 434, 3, 8, 18, 3, 8, 3, L.DCT, L.SADCT, L.HAAR)
+    assert nests(2, q1, q2)[0] and nests(4, q1, q2)[0]
+    ok, b1, b2 = nests(8, q1, q2)
+    assert not ok
+    assert sum(1 for b in b1 if b[1] > b[0]) == 7 and sum(1 for b in b2 if b[1] > b[0]) == 8
