@@ -1361,6 +1361,10 @@ static int step_host(lfbm5d_ctx *ctx, int step, const lfbm5d_params *p, float *c
     if (step == 2 && ctx->basic.ensure(asize * each * 4)) return 1;
     const bool docolor = p->chnls == 3 && p->color_space != LFBM5D_RGB;
     if (docolor && (ctx->rt_noisy.ensure(asize * each * 4) || (step == 2 && ctx->rt_basic.ensure(asize * each * 4)))) return 1;
+    // The constant tables of the step go to the device first: a change of tables needs a device-wide synchronisation (ensure_tables),
+    // and from inside step_begin it would wait for every upload queued below — the first window would start after the whole light
+    // field had arrived instead of after its nine SAIs. Here nothing is in flight yet; step_begin then finds the tables in place.
+    if (setup_tables(ctx, step, p, p->tau_4D)) return 1;
     HostIO &io = ctx->io;
     while (io.up.size() < asize) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); io.up.push_back(e); }
     while (io.fin.size() < asize) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); io.fin.push_back(e); }
