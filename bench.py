@@ -543,12 +543,21 @@ def run_reference(args):
     v = float(np.mean([x["value"] for x in vals]))
     cpu = dict(vals[-1])
     cpu["value"] = v
+    # nb_threads = 1 is the algorithm the GPU path implements (the multi-thread path tiles the SAIs and drops halo contributions,
+    # SURVEY A9): its rate and its PSNR beside the tiled run's on the SAME small sample (128^2 SAIs keep a single thread within the
+    # time budget; the 24-pixel padding weighs more on them than on 1024^2 SAIs, so both rates of this pair are pessimistic)
+    one = None
+    if os.environ.get("LFBM5D_REF_ONE_THREAD", "1") != "0":
+        s_one, s_all = cpu_sample(size=128, mode="one"), cpu_sample(size=128, mode="all")
+        one = {"nb_threads_1": {k: s_one[k] for k in ("value", "unit", "cores", "seconds", "psnr_sample", "sample")},
+               "all_cores_same_sample": {k: s_all[k] for k in ("value", "unit", "cores", "seconds", "psnr_sample")},
+               "tiling_costs_db": s_one["psnr_sample"]["denoised"] - s_all["psnr_sample"]["denoised"]}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "LF Mpix/s",
                       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
                       "ms_per_step_is": "wall time of one bounded sample (cpu_baseline.sample); value = light-field pixels / (sample time x cpu_baseline extrapolation factor)",
                       "extrapolated_ms_per_light_field": 1e3 * float(np.mean([x["extrapolated_s_per_lf"] for x in vals])),
                       "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": config_dict(world), "cpu_baseline": cpu,
+                      "config": config_dict(world), "cpu_baseline": cpu, "exact_algorithm_sample": one,
                       "e2e": {"value": v, "unit": "LF Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
