@@ -22,6 +22,14 @@ void lfio_psnr(const float *a, const float *b, size_t n, float *psnr, float *rms
  * lfio_png_read with out == NULL only reports the size. Return 0 on success, 1 on error. */
 int lfio_png_read(const char *name, float *out, size_t capacity, size_t *w, size_t *h, size_t *c);
 int lfio_png_write(const char *name, const float *data, size_t w, size_t h, size_t c);
+/* load_LF / save_LF (utilities_LF.cpp:72-231): <dir>/<sub><sep>%02d<sep>%02d.png for s in [s_start, s_start + aheight), t likewise; the
+ * light field as [asize][c*W*H] floats with st ordered per ang_major (LFBM5D_ROWMAJOR / LFBM5D_COLMAJOR); mask[st] = 1 where an image
+ * holds a non-zero sample; a gray image stored as RGB counts one channel. Files are decoded / encoded on the host cores
+ * (LFBM5D_IO_THREADS). lfio_load_LF with out == NULL only reports width / height / chnls of the first image and the mask. */
+int lfio_load_LF(const char *dir, const char *sub, const char *sep, unsigned ang_major, unsigned awidth, unsigned aheight, unsigned s_start,
+                 unsigned t_start, float *out, size_t capacity, unsigned *mask, unsigned *width, unsigned *height, unsigned *chnls);
+int lfio_save_LF(const char *dir, const char *sub, const char *sep, const float *lf, const unsigned *mask, unsigned ang_major, unsigned awidth,
+                 unsigned aheight, unsigned s_start, unsigned t_start, unsigned width, unsigned height, unsigned chnls);
 /* compute_psnr_LF (utilities_LF.cpp:639-700), compute_diff_LF (:702-745) and write_psnr_LF (:782-869) on light fields stored as
  * [asize][each] floats; stats4 = (avg psnr, std psnr, avg rmse, std rmse). The report is appended to file_name. */
 int lfio_psnr_LF(const float *lf1, const float *lf2, const unsigned *mask, unsigned asize, size_t each, float *psnr, float *rmse, float *stats4);

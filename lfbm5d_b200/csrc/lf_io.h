@@ -5,6 +5,7 @@
 // (utilities_LF.cpp:782-869). Header only.
 #pragma once
 #include <zlib.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -17,10 +18,28 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <sys/time.h>
 #include <unistd.h>
 
 namespace lfio {
+
+// SAIs are independent files / arrays: decode, encode and noise generation run on the host cores (the reference does the same with
+// `#pragma omp parallel for`, utilities_LF.cpp:102, :255). LFBM5D_IO_THREADS=<n> sets the number of threads (1 = sequential).
+template <class F> inline void parallel_for(unsigned n, F fn)
+{
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("LFBM5D_IO_THREADS")) nt = (unsigned) atoi(e);
+    nt = std::max(1u, std::min(std::min(nt, 32u), n));
+    if (nt <= 1) { for (unsigned i = 0; i < n; i++) fn(i); return; }
+    std::atomic<unsigned> next(0);
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++)
+        pool.emplace_back([&]() { for (unsigned i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
+    for (auto &th : pool) th.join();
+}
 
 // ---------------------------------------------------------------- PNG
 inline uint32_t be32(const unsigned char *p) { return ((uint32_t) p[0] << 24) | ((uint32_t) p[1] << 16) | ((uint32_t) p[2] << 8) | p[3]; }
@@ -166,30 +185,37 @@ inline int load_LF(const char *dir, const char *sub, const char *sep, std::vecto
                    unsigned ang_major, unsigned awidth, unsigned aheight, unsigned s_start, unsigned t_start, unsigned *width,
                    unsigned *height, unsigned *chnls, unsigned ROW)
 {
-    LF.assign(awidth * aheight, std::vector<float>());
-    mask.assign(awidth * aheight, 0u);
+    const unsigned asize = awidth * aheight;
+    LF.assign(asize, std::vector<float>());
+    mask.assign(asize, 0u);
     std::cout << std::endl;
-    for (unsigned s = 0; s < aheight; s++)
-        for (unsigned t = 0; t < awidth; t++) {
-            const std::string name = sai_path(dir, sub, sep, s + s_start, t + t_start);
-            std::cout << "\rRead input image " << name << std::flush;
-            size_t w = 0, h = 0, c = 0;
-            std::vector<float> tmp;
-            if (!read_png_f32(name, tmp, w, h, c)) {
-                std::cout << std::endl << "error :: " << name << " not found or not a correct png image." << dir << " folder might not exist." << std::endl;
-                return EXIT_FAILURE;      // (the reference prints and then dereferences a null pointer here, utilities_LF.cpp:117-124)
-            }
-            if (c > 2) {       // grey image stored as colour (utilities_LF.cpp:123-130)
-                size_t k = 0;
-                float acc = 0.0f;
-                while (k < w * h && tmp[k] == tmp[w * h + k] && tmp[k] == tmp[2 * w * h + k]) { acc += tmp[k] + tmp[w * h + k] + tmp[2 * w * h + k]; k++; }
-                c = (k == w * h && acc > 0.0f) ? 1 : 3;
-            }
-            if (s == 0 && t == 0) { *width = (unsigned) w; *height = (unsigned) h; *chnls = (unsigned) c; }
-            const unsigned st = ang_major == ROW ? s * awidth + t : s + t * aheight;
-            LF[st].assign(tmp.begin(), tmp.begin() + w * h * c);
-            for (size_t k = 0; k < w * h * c; k++) if (tmp[k]) { mask[st] = 1; break; }      // utilities_LF.cpp:149-154
+    std::mutex out_mu;
+    std::vector<std::string> failed(asize);
+    std::vector<unsigned> dims(3 * (size_t) asize, 0u);
+    parallel_for(asize, [&](unsigned q) {
+        const unsigned s = q / awidth, t = q % awidth;
+        const std::string name = sai_path(dir, sub, sep, s + s_start, t + t_start);
+        { std::lock_guard<std::mutex> lk(out_mu); std::cout << "\rRead input image " << name << std::flush; }
+        size_t w = 0, h = 0, c = 0;
+        std::vector<float> tmp;
+        if (!read_png_f32(name, tmp, w, h, c)) { failed[q] = name; return; }
+        if (c > 2) {       // grey image stored as colour (utilities_LF.cpp:123-130)
+            size_t k = 0;
+            float acc = 0.0f;
+            while (k < w * h && tmp[k] == tmp[w * h + k] && tmp[k] == tmp[2 * w * h + k]) { acc += tmp[k] + tmp[w * h + k] + tmp[2 * w * h + k]; k++; }
+            c = (k == w * h && acc > 0.0f) ? 1 : 3;
         }
+        dims[3 * q] = (unsigned) w; dims[3 * q + 1] = (unsigned) h; dims[3 * q + 2] = (unsigned) c;
+        const unsigned st = ang_major == ROW ? s * awidth + t : s + t * aheight;
+        LF[st].assign(tmp.begin(), tmp.begin() + w * h * c);
+        for (size_t k = 0; k < w * h * c; k++) if (tmp[k]) { mask[st] = 1; break; }      // utilities_LF.cpp:149-154
+    });
+    for (unsigned q = 0; q < asize; q++)
+        if (!failed[q].empty()) {
+            std::cout << std::endl << "error :: " << failed[q] << " not found or not a correct png image." << dir << " folder might not exist." << std::endl;
+            return EXIT_FAILURE;      // (the reference prints and then dereferences a null pointer here, utilities_LF.cpp:117-124)
+        }
+    *width = dims[0]; *height = dims[1]; *chnls = dims[2];      // of the first image (s = t = 0), utilities_LF.cpp:133-138
     std::cout << std::endl << " Light field size :" << std::endl << " - awidth         = " << awidth << std::endl << " - aheight        = " << aheight << std::endl
               << " - width          = " << *width << std::endl << " - height         = " << *height << std::endl << " - nb of channels = " << *chnls << std::endl;
     return EXIT_SUCCESS;
@@ -198,15 +224,18 @@ inline int save_LF(const char *dir, const char *sub, const char *sep, const std:
                    unsigned ang_major, unsigned awidth, unsigned aheight, unsigned s_start, unsigned t_start, unsigned width,
                    unsigned height, unsigned chnls, unsigned ROW)
 {
-    for (unsigned s = 0; s < aheight; s++)
-        for (unsigned t = 0; t < awidth; t++) {
-            const unsigned st = ang_major == ROW ? s * awidth + t : s + t * aheight;
-            if (!mask[st]) continue;
-            const std::string name = sai_path(dir, sub, sep, s + s_start, t + t_start);
-            if (!write_png_f32(name, LF[st].data(), width, height, chnls)) {
-                std::cout << "... failed to save png image " << name << std::endl;
-                return EXIT_FAILURE;
-            }
+    const unsigned asize = awidth * aheight;
+    std::vector<char> bad(asize, 0);
+    parallel_for(asize, [&](unsigned q) {
+        const unsigned s = q / awidth, t = q % awidth;
+        const unsigned st = ang_major == ROW ? s * awidth + t : s + t * aheight;
+        if (!mask[st]) return;
+        if (!write_png_f32(sai_path(dir, sub, sep, s + s_start, t + t_start), LF[st].data(), width, height, chnls)) bad[q] = 1;
+    });
+    for (unsigned q = 0; q < asize; q++)
+        if (bad[q]) {
+            std::cout << "... failed to save png image " << sai_path(dir, sub, sep, q / awidth + s_start, q % awidth + t_start) << std::endl;
+            return EXIT_FAILURE;
         }
     return EXIT_SUCCESS;
 }
@@ -236,18 +265,21 @@ struct MT {
 inline void add_noise_LF(const std::vector<std::vector<float> > &LF, const std::vector<unsigned> &mask, std::vector<std::vector<float> > &noisy, float sigma)
 {
     const char *fixed = getenv("LFBM5D_SEED");
-    for (size_t st = 0; st < LF.size(); st++) {
-        if (!mask[st]) continue;
+    struct timeval tp;
+    gettimeofday(&tp, nullptr);
+    const unsigned long seed0 = fixed ? strtoul(fixed, nullptr, 10) : (unsigned long) (tp.tv_sec * 1000 + tp.tv_usec / 1000) + (unsigned long) getpid();
+    if (noisy.size() < LF.size()) noisy.resize(LF.size());
+    parallel_for((unsigned) LF.size(), [&](unsigned st) {
+        if (!mask[st]) return;
         MT g;
-        if (fixed) g.seed(strtoul(fixed, nullptr, 10) + st);
-        else { struct timeval tp; gettimeofday(&tp, nullptr); g.seed((unsigned long) (tp.tv_sec * 1000 + tp.tv_usec / 1000) + (unsigned long) getpid() + st); }
+        g.seed(seed0 + st);
         noisy[st].resize(LF[st].size());
         for (size_t k = 0; k < LF[st].size(); k++) {
             const double a = g.res53(), b = g.res53();
             const double z = (double) sigma * sqrt(-2.0 * log(a)) * cos(2.0 * M_PI * b);
             noisy[st][k] = LF[st][k] + (float) z;
         }
-    }
+    });
 }
 
 // ---------------------------------------------------------------- metrics

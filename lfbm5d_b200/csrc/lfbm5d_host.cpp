@@ -157,6 +157,36 @@ int lfio_png_write(const char *name, const float *data, size_t w, size_t h, size
     return name && data && lfio::write_png_f32(name, data, w, h, c) ? 0 : 1;
 }
 
+// load_LF / save_LF (utilities_LF.cpp:72-231) on a light field stored as [asize][c*W*H] floats (st ordered per ang_major). With
+// out == NULL lfio_load_LF only reports the size of the first image and the mask.
+int lfio_load_LF(const char *dir, const char *sub, const char *sep, unsigned ang_major, unsigned awidth, unsigned aheight, unsigned s_start,
+                 unsigned t_start, float *out, size_t capacity, unsigned *mask, unsigned *width, unsigned *height, unsigned *chnls)
+{
+    std::vector<std::vector<float> > LF;
+    std::vector<unsigned> m;
+    if (lfio::load_LF(dir, sub, sep, LF, m, ang_major, awidth, aheight, s_start, t_start, width, height, chnls, LFBM5D_ROWMAJOR) != EXIT_SUCCESS) return 1;
+    const size_t each = (size_t) *width * *height * *chnls;
+    if (mask) memcpy(mask, m.data(), m.size() * sizeof(unsigned));
+    if (out) {
+        if (capacity < each * LF.size()) return 1;
+        for (size_t st = 0; st < LF.size(); st++) {
+            if (LF[st].size() != each) return 1;       // every image must have the size of the first one
+            memcpy(out + st * each, LF[st].data(), each * sizeof(float));
+        }
+    }
+    return 0;
+}
+
+static std::vector<std::vector<float> > lf_of(const float *a, unsigned asize, size_t each);
+
+int lfio_save_LF(const char *dir, const char *sub, const char *sep, const float *lf, const unsigned *mask, unsigned ang_major, unsigned awidth,
+                 unsigned aheight, unsigned s_start, unsigned t_start, unsigned width, unsigned height, unsigned chnls)
+{
+    const unsigned asize = awidth * aheight;
+    return lfio::save_LF(dir, sub, sep, lf_of(lf, asize, (size_t) width * height * chnls), std::vector<unsigned>(mask, mask + asize), ang_major, awidth, aheight,
+                         s_start, t_start, width, height, chnls, LFBM5D_ROWMAJOR) == EXIT_SUCCESS ? 0 : 1;
+}
+
 static std::vector<std::vector<float> > lf_of(const float *a, unsigned asize, size_t each)
 {
     std::vector<std::vector<float> > v(asize);

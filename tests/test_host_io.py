@@ -205,3 +205,116 @@ def test_metrics_and_report_equal_the_reference(tmp_path, ref, major):
                      fp(rm), float(st[2]), float(st[3])) == 0
         files[name] = path.read_bytes()
     assert files["ours"] == files["ref"] and b"No SAI" in files["ours"]
+
+
+def _write_lf(tmp_path, arr, s_start=1, t_start=1, gray=False):
+    """arr [ah, aw, C, H, W] uint8 -> <tmp>/SAI_%02d_%02d.png"""
+    from PIL import Image
+    ah, aw = arr.shape[:2]
+    for s in range(ah):
+        for t in range(aw):
+            a = arr[s, t]
+            im = Image.fromarray(a[0]) if gray else Image.fromarray(a.transpose(1, 2, 0))
+            im.save(str(tmp_path / ("SAI_%02d_%02d.png" % (s + s_start, t + t_start))))
+
+
+def _load_lf(d, aw, ah, major, s_start=1, t_start=1):
+    h = host()
+    h.lfio_load_LF.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_float), C.c_size_t,
+                               C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    w, hh, c = C.c_uint(), C.c_uint(), C.c_uint()
+    mask = np.zeros(aw * ah, np.uint32)
+    mp = mask.ctypes.data_as(C.POINTER(C.c_uint))
+    if h.lfio_load_LF(str(d).encode(), b"SAI", b"_", major, aw, ah, s_start, t_start, None, 0, mp, C.byref(w), C.byref(hh), C.byref(c)) != 0:
+        return None
+    out = np.zeros((aw * ah, c.value, hh.value, w.value), np.float32)
+    assert h.lfio_load_LF(str(d).encode(), b"SAI", b"_", major, aw, ah, s_start, t_start, out.ctypes.data_as(C.POINTER(C.c_float)), out.size, mp,
+                          C.byref(w), C.byref(hh), C.byref(c)) == 0
+    return out, mask
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_load_and_save_light_field(tmp_path, monkeypatch, threads):
+    """load_LF / save_LF (utilities_LF.cpp:72-231): file naming with start indices, row / column major ordering, the mask of empty SAIs
+    (:149-154), a gray image stored as RGB counting one channel (:123-130), masked SAIs not written; same result on one thread and
+    on several (the files are decoded / encoded on the host cores)."""
+    from PIL import Image
+    monkeypatch.setenv("LFBM5D_IO_THREADS", threads)
+    rng = np.random.default_rng(3)
+    aw, ah, H, W = 3, 2, 11, 14
+    arr = rng.integers(1, 256, size=(ah, aw, 3, H, W)).astype(np.uint8)
+    arr[1, 0] = 0                                        # an empty SAI
+    src = tmp_path / "src"
+    src.mkdir()
+    _write_lf(src, arr, s_start=2, t_start=5)
+    for major, order in ((L.ROWMAJOR, lambda s, t: s * aw + t), (L.COLMAJOR, lambda s, t: s + t * ah)):
+        lf, mask = _load_lf(src, aw, ah, major, 2, 5)
+        assert lf.shape == (6, 3, H, W)
+        for s in range(ah):
+            for t in range(aw):
+                assert np.array_equal(lf[order(s, t)], arr[s, t].astype(np.float32))
+                assert mask[order(s, t)] == (0 if (s, t) == (1, 0) else 1)
+    assert _load_lf(src, aw + 1, ah, L.ROWMAJOR, 2, 5) is None          # SAI_02_08.png does not exist
+    # gray stored as RGB -> one channel
+    g = tmp_path / "gray"
+    g.mkdir()
+    garr = np.repeat(rng.integers(1, 256, size=(1, 2, 1, H, W)).astype(np.uint8), 3, axis=2)
+    _write_lf(g, garr)
+    lf, mask = _load_lf(g, 2, 1, L.ROWMAJOR)
+    assert lf.shape == (2, 1, H, W) and np.array_equal(lf[1, 0], garr[0, 1, 0].astype(np.float32))
+    # save: rounded floor(x + .5), clamped; the masked SAI gets no file
+    h = host()
+    h.lfio_save_LF.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_uint), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                               C.c_uint, C.c_uint, C.c_uint]
+    out = tmp_path / "out"
+    out.mkdir()
+    lf, mask = _load_lf(src, aw, ah, L.COLMAJOR, 2, 5)
+    lf = (lf + rng.normal(0, 30, lf.shape)).astype(np.float32)
+    assert h.lfio_save_LF(str(out).encode(), b"SAI", b"_", lf.ctypes.data_as(C.POINTER(C.c_float)), mask.ctypes.data_as(C.POINTER(C.c_uint)), L.COLMAJOR,
+                          aw, ah, 1, 1, W, H, 3) == 0
+    assert sorted(os.listdir(str(out))) == ["SAI_%02d_%02d.png" % (s + 1, t + 1) for s in range(ah) for t in range(aw) if (s, t) != (1, 0)]
+    for s in range(ah):
+        for t in range(aw):
+            if (s, t) == (1, 0):
+                continue
+            img = np.asarray(Image.open(str(out / ("SAI_%02d_%02d.png" % (s + 1, t + 1))))).transpose(2, 0, 1)
+            assert np.array_equal(img, np.clip(np.floor(lf[s + t * ah] + np.float32(0.5)), 0, 255).astype(np.uint8))
+
+
+def test_cli_front_half_without_a_gpu(tmp_path):
+    """LFBM5Ddenoising up to the first GPU call, wherever it runs: PNGs read, noise added with LFBM5D_SEED, noisy light field and the
+    first report block written — identical on one I/O thread and on several, and equal to the library's own noise — and, on a machine
+    without a CUDA device, a clean failure instead of a CPU fallback."""
+    import re
+    import subprocess
+    from PIL import Image
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(ROOT, "lfbm5d_b200", "_lib", "LFBM5Ddenoising")
+    rng = np.random.default_rng(9)
+    arr = rng.integers(0, 256, size=(3, 3, 3, 40, 48)).astype(np.uint8)
+    src = tmp_path / "sourceLF"
+    src.mkdir()
+    _write_lf(src, arr)
+    outs = {}
+    for threads in ("1", "6"):
+        base = tmp_path / ("run" + threads)
+        base.mkdir()
+        for d in ("noisyLF", "basicLF", "denoisedLF", "diffLF"):
+            (base / d).mkdir()
+        args = [exe, str(src), "SAI", "_", "3", "3", "1", "1", "1", "1", "row", "25", "2.7", str(base / "noisyLF"), str(base / "basicLF"),
+                str(base / "denoisedLF"), str(base / "diffLF"), "8", "18", "6", "16", "4", "id", "sadct", "haar", "0", "16", "18", "6", "8", "4", "dct",
+                "sadct", "haar", "0", "opp", "0", str(base / "report.txt")]
+        env = dict(os.environ, LFBM5D_SEED="77", LFBM5D_IO_THREADS=threads)
+        p = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=600)
+        txt = p.stdout.decode()
+        assert " - nb of channels = 3" in txt and " - width          = 48" in txt
+        import torch
+        if not torch.cuda.is_available():
+            assert p.returncode == 1 and "THIS IS THE END" not in txt          # no CPU fallback
+        noisy = np.stack([np.asarray(Image.open(str(base / "noisyLF" / ("SAI_%02d_%02d.png" % (s + 1, t + 1))))).transpose(2, 0, 1)
+                          for s in range(3) for t in range(3)])
+        outs[threads] = (noisy, (base / "report.txt").read_text().split("-> Average RMSE")[0])
+    assert np.array_equal(outs["1"][0], outs["6"][0]) and outs["1"][1] == outs["6"][1]
+    want = L.add_noise(arr.reshape(9, 3, 40, 48).astype(np.float32), 25.0, seed0=77)
+    assert np.array_equal(outs["1"][0], np.clip(np.floor(want + np.float32(0.5)), 0, 255).astype(np.uint8))
+    assert re.search(r"-> Average PSNR noisy = [0-9.]+", outs["1"][1])
