@@ -281,15 +281,16 @@ def test_load_and_save_light_field(tmp_path, monkeypatch, threads):
             assert np.array_equal(img, np.clip(np.floor(lf[s + t * ah] + np.float32(0.5)), 0, 255).astype(np.uint8))
 
 
-def test_cli_front_half_without_a_gpu(tmp_path):
-    """LFBM5Ddenoising up to the first GPU call, wherever it runs: PNGs read, noise added with LFBM5D_SEED, noisy light field and the
+@pytest.mark.parametrize("driver", ["LFBM5Ddenoising", "LFBM3Ddenoising"])
+def test_cli_front_half_without_a_gpu(tmp_path, driver):
+    """Both command lines up to the first GPU call, wherever it runs: PNGs read, noise added with LFBM5D_SEED, noisy light field and the
     first report block written — identical on one I/O thread and on several, and equal to the library's own noise — and, on a machine
     without a CUDA device, a clean failure instead of a CPU fallback."""
     import re
     import subprocess
     from PIL import Image
     ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(ROOT, "lfbm5d_b200", "_lib", "LFBM5Ddenoising")
+    exe = os.path.join(ROOT, "lfbm5d_b200", "_lib", driver)
     rng = np.random.default_rng(9)
     arr = rng.integers(0, 256, size=(3, 3, 3, 40, 48)).astype(np.uint8)
     src = tmp_path / "sourceLF"
@@ -302,8 +303,12 @@ def test_cli_front_half_without_a_gpu(tmp_path):
         for d in ("noisyLF", "basicLF", "denoisedLF", "diffLF"):
             (base / d).mkdir()
         args = [exe, str(src), "SAI", "_", "3", "3", "1", "1", "1", "1", "row", "25", "2.7", str(base / "noisyLF"), str(base / "basicLF"),
-                str(base / "denoisedLF"), str(base / "diffLF"), "8", "18", "6", "16", "4", "id", "sadct", "haar", "0", "16", "18", "6", "8", "4", "dct",
-                "sadct", "haar", "0", "opp", "0", str(base / "report.txt")]
+                str(base / "denoisedLF"), str(base / "diffLF")]
+        if driver == "LFBM5Ddenoising":      # README.md:50
+            args += ["8", "18", "6", "16", "4", "id", "sadct", "haar", "0", "16", "18", "6", "8", "4", "dct", "sadct", "haar", "0", "opp", "0"]
+        else:                                # README.md:62 (main_bm3d_LF.cpp)
+            args += ["16", "16", "8", "3", "bior", "0", "32", "16", "8", "3", "dct", "0", "opp", "0"]
+        args.append(str(base / "report.txt"))
         env = dict(os.environ, LFBM5D_SEED="77", LFBM5D_IO_THREADS=threads)
         p = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=600)
         txt = p.stdout.decode()
